@@ -1,0 +1,112 @@
+/* Plain-C restatement of the quantiser arithmetic — TEST INFRASTRUCTURE, NOT A PRODUCT PATH.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library.
+ *
+ * It follows the reference's formulas (models/vq_vae.py:30-35 distances+argmin, :43 gather,
+ * :47-53 losses + straight-through, autograd of those for the gradients; models/mcq_vae.py:104,117
+ * the overlapping channel slices [:, i:i+d]) but fixes ONE evaluation order for every sum — the
+ * order the CUDA kernels are specified to use (DESIGN.md "arithmetic contract"):
+ *     |z|^2, |e|^2, z.e :  acc = fmaf(a_j, b_j, acc), j ascending from 0, acc starts at 0
+ *     dist  = (zz + ee_k) - 2*dot          two fp32 roundings, the reference's association
+ *     argmin: ascending k, strict '<' (first minimum wins); the first NaN wins over any number
+ * so the GPU kernels can be held bit-exact against it on EVERY row, while the comparison against
+ * the reference proper (ATen sgemm order; oracle/ctvq_oracle.py + tests/golden) allows only
+ * counted near-ties.  Pinned by tests/test_oracle_golden.py::test_c_oracle_* against the goldens.
+ *
+ * Layout: latents NCHW [B, Dtot, HW]; codebook c is [K, d] and reads channels c*cs .. c*cs+d-1;
+ * quantised output [B, C*d, HW]; indices int64 [B, C, HW].
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+static float dot_seq(const float *a, long sa, const float *b, long sb, int d) {
+    float acc = 0.0f;
+    for (int j = 0; j < d; ++j) acc = fmaf(a[j * sa], b[j * sb], acc);
+    return acc;
+}
+
+/* models/vq_vae.py:30-35 (mcq_vae.py:31-39 per codebook, :104 slice) */
+void ctvq_c_argmin(const float *z, const float *const *E, int64_t B, int Dtot, int HW, int C, int d, int K,
+                   int cs, int64_t *idx_out) {
+    float *ee = (float *)malloc(sizeof(float) * (size_t)K);
+    for (int c = 0; c < C; ++c) {
+        const float *Ec = E[c];
+        for (int k = 0; k < K; ++k) ee[k] = dot_seq(Ec + (long)k * d, 1, Ec + (long)k * d, 1, d);
+        for (int64_t b = 0; b < B; ++b)
+            for (int p = 0; p < HW; ++p) {
+                const float *zr = z + ((b * Dtot + (long)c * cs) * HW + p);
+                float zz = dot_seq(zr, HW, zr, HW, d);
+                float best = 0.0f;
+                int bi = -1;
+                for (int k = 0; k < K; ++k) {
+                    float dot = dot_seq(zr, HW, Ec + (long)k * d, 1, d);
+                    float dist = (zz + ee[k]) - 2.0f * dot;
+                    int take = (bi < 0) || (dist < best) || (dist != dist && best == best);
+                    if (take) { best = dist; bi = k; }
+                }
+                idx_out[(b * C + c) * HW + p] = bi;
+            }
+    }
+    free(ee);
+}
+
+/* models/vq_vae.py:43-55 (mcq_vae.py:45-64 per codebook, :117-125 slice/cat/sum) */
+void ctvq_c_gather_st_loss(const float *z, const float *const *E, const int64_t *idx, int64_t B, int Dtot, int HW,
+                           int C, int d, int K, int cs, float beta, float *q_out, float *loss_out /* [C+1] */) {
+    (void)K;
+    float total = 0.0f;
+    for (int c = 0; c < C; ++c) {
+        double acc = 0.0;
+        for (int64_t b = 0; b < B; ++b)
+            for (int p = 0; p < HW; ++p) {
+                const float *e = E[c] + idx[(b * C + c) * HW + p] * d;
+                for (int j = 0; j < d; ++j) {
+                    float zv = z[(b * Dtot + (long)c * cs + j) * HW + p];
+                    float diff = e[j] - zv;
+                    q_out[(b * (long)C * d + (long)c * d + j) * HW + p] = zv + diff;
+                    acc += (double)(diff * diff);
+                }
+            }
+        float m = (float)(acc / ((double)B * HW * d));
+        loss_out[c] = m * beta + m;
+        total = total + loss_out[c];
+    }
+    loss_out[C] = total;
+}
+
+/* autograd of models/vq_vae.py:43-53; overlap accumulation for models/mcq_vae.py:117 slices */
+void ctvq_c_backward(const float *z, const float *const *E, const int64_t *idx, const float *g_out, float g_loss,
+                     int64_t B, int Dtot, int HW, int C, int d, int K, int cs, float beta, float *gz /* [B,Dtot,HW] */,
+                     float *gE /* [C,K,d] */) {
+    double nd = (double)B * HW * d;
+    memset(gz, 0, sizeof(float) * (size_t)(B * Dtot * HW));
+    double *acc = (double *)calloc((size_t)C * K * d, sizeof(double));
+    for (int c = 0; c < C; ++c)
+        for (int64_t b = 0; b < B; ++b)
+            for (int p = 0; p < HW; ++p) {
+                int64_t k = idx[(b * C + c) * HW + p];
+                const float *e = E[c] + k * d;
+                for (int j = 0; j < d; ++j) {
+                    long zi = (b * Dtot + (long)c * cs + j) * HW + p;
+                    float diff = e[j] - z[zi];
+                    gz[zi] += g_out[(b * (long)C * d + (long)c * d + j) * HW + p] +
+                              (float)(-2.0 * beta / nd) * g_loss * diff;
+                    acc[((long)c * K + k) * d + j] += (double)diff;
+                }
+            }
+    for (long i = 0; i < (long)C * K * d; ++i) gE[i] = (float)((2.0 / nd) * g_loss * acc[i]);
+    free(acc);
+}
+
+/* models/vanilla_vae.py:115-117 (eps supplied) and :143 */
+void ctvq_c_reparam_kld(const float *mu, const float *lv, const float *eps, int64_t B, int L, float *z_out,
+                        float *kld_out) {
+    double acc = 0.0;
+    for (int64_t i = 0; i < B * L; ++i) {
+        z_out[i] = eps[i] * expf(0.5f * lv[i]) + mu[i];
+        acc += (double)(1.0f + lv[i] - mu[i] * mu[i] - expf(lv[i]));
+    }
+    *kld_out = (float)(-0.5 * acc / (double)B);
+}
