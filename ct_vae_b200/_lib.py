@@ -1,0 +1,97 @@
+"""ctypes binding of libctvq.so (include/ctvq.h).  There is NO fallback: if the library is missing or a
+tensor is not on a CUDA device the ops raise."""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libctvq.so")
+_lib = None
+_lock = threading.Lock()
+
+PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
+F32, BF16 = 0, 1
+
+_vp, _i, _i64, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float
+_SIGNATURES = {
+    "ctvq_version": (_i, []),
+    "ctvq_strerror": (ctypes.c_char_p, [_i]),
+    "ctvq_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ctvq_set_path": (_i, [_i]),
+    "ctvq_last_path": (_i, []),
+    "ctvq_argmin": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_gather_st_loss": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_forward": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_reparam_kld_fwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_reparam_kld_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp]),
+    "ctvq_nccl_load": (_i, [ctypes.c_char_p]),
+    "ctvq_nccl_unique_id": (_i, [_vp]),
+    "ctvq_nccl_comm_init": (_i, [ctypes.POINTER(_vp), _i, _i, _vp, _i]),
+    "ctvq_nccl_comm_destroy": (_i, [_vp]),
+    "ctvq_allreduce_codebook_grad": (_i, [_vp, _vp, _sz, _f, _i, _vp]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """Load libctvq.so (built by ``__graft_entry__.build()`` / ``make -C ct_vae_b200/csrc``)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"ct_vae_b200: {LIB_PATH} is missing — build it with `python -c 'import __graft_entry__ as g; "
+                        "g.build()'` (there is no CPU or PyTorch fallback for the quantiser path)")
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "ctvq"):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {lib().ctvq_strerror(rc).decode()}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ct_vae_b200 ops run on CUDA tensors only — there is no CPU fallback "
+                               f"(got a tensor on {t.device})")
+
+
+_workspaces = {}
+
+
+def workspace(device: torch.device, stream_ptr: int) -> torch.Tensor:
+    """Zero-initialised per-(device, stream) scratch the kernels keep self-cleaning."""
+    key = (device.index, stream_ptr)
+    ws = _workspaces.get(key)
+    if ws is None:
+        n = lib().ctvq_workspace_bytes(64, 0, 0)
+        ws = torch.zeros(n, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def set_path(path: int) -> int:
+    return lib().ctvq_set_path(path)
+
+
+def last_path() -> int:
+    return lib().ctvq_last_path()

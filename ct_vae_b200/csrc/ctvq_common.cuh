@@ -1,0 +1,77 @@
+// Shared declarations of the ctvq kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ctvq.h"
+
+namespace ctvq {
+
+// Kernel-parameter block: everything by value so a launch needs no device-side pointer table
+// (CUDA-graph friendly; codebooks stay separate nn.Parameters as in models/mcq_vae.py:94-97).
+struct QuantParams {
+    const float* z[CTVQ_MAX_SEGMENTS];
+    long long* idx[CTVQ_MAX_SEGMENTS];  // int64 [B, C, HW] per segment (written by argmin, read by gather)
+    const float* E[CTVQ_MAX_CODEBOOKS];
+    float* q;         // [B, C*d, HW]
+    float* loss_out;  // [C+1]
+    double* loss_acc; // workspace [C]
+    unsigned int* ticket;  // workspace
+    unsigned int* err;     // workspace: bit0 = index out of range seen
+    long long B;      // images per segment
+    long long N;      // rows per segment = B*HW
+    int n_seg, Dtot, HW, C, d, K, cs;
+    int tiles_per_seg;
+    float beta;
+    int fused;  // 0: argmin only, 1: argmin + gather + loss
+};
+
+struct Workspace {  // layout of the caller-provided zero-initialised buffer
+    double loss_acc[CTVQ_MAX_CODEBOOKS];
+    double kld_acc;
+    unsigned int ticket;
+    unsigned int ticket2;
+    unsigned int err;
+    unsigned int pad;
+};
+
+__device__ __forceinline__ bool lex_better(float d1, int i1, float d2, int i2) {
+    // true when (d1,i1) must replace (d2,i2): smaller value, ties -> smaller index, first NaN wins
+    // (torch.argmin semantics, models/vq_vae.py:35)
+    const bool n1 = d1 != d1, n2 = d2 != d2;
+    if (n1 | n2) return n1 && (!n2 || i1 < i2);
+    return d1 < d2 || (d1 == d2 && i1 < i2);
+}
+
+__device__ __forceinline__ float dist_f32(float zz, float ee, float dot) {
+    // (|z|^2 + |e|^2) - 2 z.e : the reference's association (models/vq_vae.py:30-32), no contraction
+    return __fsub_rn(__fadd_rn(zz, ee), __fmul_rn(2.0f, dot));
+}
+
+struct BwdParams {
+    const float* z;
+    const long long* idx;
+    const float* g_out;   // may be null
+    const float* g_loss;  // device scalar
+    const float* E[CTVQ_MAX_CODEBOOKS];
+    float* gz;  // [B, Dtot, HW]
+    float* gE;  // [C, K, d] (zeroed by the launcher before the kernel)
+    unsigned int* err;
+    long long B, N;
+    int Dtot, HW, C, d, K, cs;
+    float beta;
+    int smem_acc;  // 1: privatise the [C,K,d] accumulator in shared memory
+};
+
+// launch helpers implemented in the .cu files; return 0, a cudaError_t (>0) or a CTVQ_E_* (<0)
+int launch_forward_simt(const QuantParams& p, cudaStream_t s);
+int launch_gather(const QuantParams& p, cudaStream_t s);
+int launch_backward(const BwdParams& p, cudaStream_t s);
+int launch_reparam_fwd(const float* mu, const float* lv, const float* eps, long long B, int L, float* z, float* kld,
+                       Workspace* ws, cudaStream_t s);
+int launch_reparam_bwd(const float* mu, const float* lv, const float* eps, const float* g_z, const float* g_kld,
+                       long long B, int L, float* g_mu, float* g_lv, cudaStream_t s);
+int launch_forward_tc(const QuantParams& p, cudaStream_t s);  // returns CTVQ_E_UNSUPPORTED when shape not covered
+bool tc_supported(const QuantParams& p);
+
+}  // namespace ctvq

@@ -1,0 +1,118 @@
+"""Autograd bindings of the quantiser kernels (thin: shapes, pointers, stream; all maths is in libctvq.so)."""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+
+
+def _shape(latents: Tensor, codebooks: Sequence[Tensor], chan_stride: int):
+    if latents.dim() != 4:
+        raise RuntimeError(f"latents must be [B, D, H, W], got {tuple(latents.shape)}")
+    b, dtot, h, w = latents.shape
+    k, d = codebooks[0].shape
+    c = len(codebooks)
+    for e in codebooks:
+        if tuple(e.shape) != (k, d):
+            raise RuntimeError("all codebooks must share one [K, d] shape")
+        if e.dtype != torch.float32 or not e.is_contiguous():
+            raise RuntimeError("codebooks must be contiguous float32")
+    if (c - 1) * chan_stride + d > dtot:
+        # same failure class as the reference: a size mismatch inside torch.matmul (models/mcq_vae.py:33)
+        raise RuntimeError(f"codebook slices ({c} x {d} channels, stride {chan_stride}) exceed the {dtot} latent channels")
+    if latents.dtype != torch.float32:
+        raise RuntimeError(f"latents must be float32 (the reference's arithmetic type), got {latents.dtype}")
+    return b, dtot, h, w, c, d, k
+
+
+def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], chan_stride: int = 1) -> List[Tensor]:
+    """argmin indices [B, C, H, W] int64 for each input tensor, ONE launch for up to 4 same-shape inputs.
+
+    Replaces models/mcq_vae.py:26-39 / :100-110 (and the x / y pair of models/ct_mcq_vae.py:530,536)."""
+    _lib.require_cuda(*latents_list, *codebooks)
+    zs = [z.detach().contiguous() for z in latents_list]
+    es = [e.detach() for e in codebooks]
+    b, dtot, h, w, c, d, k = _shape(zs[0], es, chan_stride)
+    for z in zs[1:]:
+        if z.shape != zs[0].shape:
+            raise RuntimeError("paired inputs must share a shape")
+    dev = zs[0].device
+    outs = [torch.empty((b, c, h, w), dtype=torch.int64, device=dev) for _ in zs]
+    sp = _lib.stream_ptr(dev)
+    ws = _lib.workspace(dev, sp)
+    rc = _lib.lib().ctvq_argmin(_lib.ptr_array(zs), len(zs), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride,
+                                _lib.F32, _lib.ptr_array(outs), ws.data_ptr(), ws.numel(), dev.index, sp)
+    _lib.check(rc, "ctvq_argmin")
+    return outs
+
+
+class _Quantize(torch.autograd.Function):
+    """(latents, codebooks[, indices]) -> (straight-through output, summed vq_loss, indices, per-codebook losses)."""
+
+    @staticmethod
+    def forward(ctx, latents: Tensor, beta: float, chan_stride: int, given_inds: Optional[Tensor], comm, *codebooks):
+        _lib.require_cuda(latents, *codebooks)
+        z = latents.detach().contiguous()
+        es = [e.detach() for e in codebooks]
+        b, dtot, h, w, c, d, k = _shape(z, es, chan_stride)
+        dev = z.device
+        out = torch.empty((b, c * d, h, w), dtype=z.dtype, device=dev)
+        losses = torch.empty(c + 1, dtype=torch.float32, device=dev)
+        sp = _lib.stream_ptr(dev)
+        ws = _lib.workspace(dev, sp)
+        L = _lib.lib()
+        if given_inds is None:
+            inds = torch.empty((b, c, h, w), dtype=torch.int64, device=dev)
+            rc = L.ctvq_forward(z.data_ptr(), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride, _lib.F32,
+                                float(beta), inds.data_ptr(), out.data_ptr(), losses.data_ptr(), ws.data_ptr(),
+                                ws.numel(), dev.index, sp)
+            _lib.check(rc, "ctvq_forward")
+        else:
+            _lib.require_cuda(given_inds)
+            if given_inds.numel() != b * c * h * w:
+                raise RuntimeError(f"indices have {given_inds.numel()} elements, expected {b * c * h * w}")
+            inds = given_inds.detach().to(torch.int64).reshape(b, c, h, w).contiguous()
+            rc = L.ctvq_gather_st_loss(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), b, dtot, h * w, c, d, k,
+                                       chan_stride, _lib.F32, float(beta), out.data_ptr(), losses.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), dev.index, sp)
+            _lib.check(rc, "ctvq_gather_st_loss")
+        ctx.save_for_backward(z, inds, *es)
+        ctx.meta = (float(beta), int(chan_stride), b, dtot, h, w, c, d, k, comm)
+        per = losses[:c]
+        ctx.mark_non_differentiable(inds, per)
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None: no zero-fill kernels, no host sync
+        return out, losses[c], inds, per
+
+    @staticmethod
+    def backward(ctx, g_out, g_loss, _g_inds, _g_per):
+        z, inds, *es = ctx.saved_tensors
+        beta, cs, b, dtot, h, w, c, d, k, comm = ctx.meta
+        dev = z.device
+        if g_loss is None:
+            g_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        g_loss = g_loss.to(torch.float32).contiguous()
+        go_ptr = None
+        if g_out is not None:
+            g_out = g_out.contiguous()
+            go_ptr = g_out.data_ptr()
+        gz = torch.empty_like(z)
+        ge = torch.empty((c, k, d), dtype=torch.float32, device=dev)
+        sp = _lib.stream_ptr(dev)
+        ws = _lib.workspace(dev, sp)
+        rc = _lib.lib().ctvq_backward(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), go_ptr, g_loss.data_ptr(), b,
+                                      dtot, h * w, c, d, k, cs, _lib.F32, beta, gz.data_ptr(), ge.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), dev.index, sp)
+        _lib.check(rc, "ctvq_backward")
+        if comm is not None:
+            comm.allreduce_(ge)  # the one collective of the path, on the backward kernel's stream
+        return (gz, None, None, None, None, *ge.unbind(0))
+
+
+def quantize(latents: Tensor, codebooks: Sequence[Tensor], beta: float, chan_stride: int = 1,
+             inds: Optional[Tensor] = None, comm=None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Fused forward (argmin + gather + loss + straight-through), or gather by the given ``inds``.
+
+    Replaces models/vq_vae.py:24-55 and models/mcq_vae.py:41-64,112-137."""
+    return _Quantize.apply(latents, beta, chan_stride, inds, comm, *codebooks)

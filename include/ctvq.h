@@ -1,0 +1,126 @@
+/* ctvq — C ABI of the B200-native codebook quantiser (drop-in boundary).
+ *
+ * The reference (Strong-AI-Lab/ct-vae) has no FFI of its own: the boundary it exposes is the Python
+ * nn.Module surface of models/vq_vae.py:7-55 and models/mcq_vae.py:7-137.  Those modules are mirrored in
+ * ct_vae_b200/modules.py, which binds THIS header through ctypes.  Every entry point below names the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.  All data pointers are DEVICE pointers to
+ *     caller-owned memory on `device`; the library allocates nothing and keeps no global mutable state
+ *     (re-entrant; the caller passes a zero-initialised workspace per stream, ctvq_workspace_bytes()).
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised (CUDA-graph safe).
+ *   - return: 0 = OK, <0 = bad argument / unsupported shape (CTVQ_E_*), >0 = a cudaError_t.
+ *     ctvq_strerror() renders either.
+ *   - layout: latents NCHW = [B, Dtot, HW] contiguous; codebook c is [K, d] row-major and reads input
+ *     channels c*chan_stride .. c*chan_stride+d-1 (the reference's `latents[:, i:i+d]`,
+ *     models/mcq_vae.py:104,117, is chan_stride = 1: overlapping slices); quantised output
+ *     [B, C*d, HW]; indices int64 [B, C, HW].
+ *   - dtype: CTVQ_F32 (the reference's only arithmetic type).  Distances are evaluated as
+ *     fl(fl(|z|^2 + |e_k|^2) - 2*dot) with every sum a sequential FMA chain over ascending channel, and
+ *     argmin takes the first minimum (NaN: first NaN) — see DESIGN.md "arithmetic contract".
+ */
+#ifndef CTVQ_H_
+#define CTVQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTVQ_VERSION 100          /* 0.1.0 */
+#define CTVQ_MAX_CODEBOOKS 64
+#define CTVQ_MAX_SEGMENTS 4
+
+#define CTVQ_F32 0
+#define CTVQ_BF16 1
+
+#define CTVQ_OK 0
+#define CTVQ_E_BADARG (-1)        /* null pointer, non-positive size, C*... inconsistent */
+#define CTVQ_E_UNSUPPORTED (-2)   /* shape or dtype this build has no kernel for */
+#define CTVQ_E_WORKSPACE (-3)     /* workspace too small */
+#define CTVQ_E_NCCL (-4)          /* NCCL not loaded / NCCL call failed */
+#define CTVQ_E_NOT_BUILT (-5)
+
+/* kernel selection for ctvq_argmin / ctvq_forward */
+#define CTVQ_PATH_AUTO 0
+#define CTVQ_PATH_SIMT 1          /* shared-memory-staged fp32 FFMA kernel */
+#define CTVQ_PATH_TC 2            /* tcgen05/TMEM distance GEMM + exact fp32 re-scoring */
+
+int ctvq_version(void);
+const char* ctvq_strerror(int rc);
+
+/* Bytes of zero-initialised device workspace one stream needs for a problem with C codebooks. */
+size_t ctvq_workspace_bytes(int C, int K, int d);
+
+/* Force a kernel path for subsequent calls on this thread's library handle (tests/bench); AUTO picks
+ * by shape.  Returns the previous value. */
+int ctvq_set_path(int path);
+/* Which path the last ctvq_argmin/ctvq_forward call on this host thread dispatched to. */
+int ctvq_last_path(void);
+
+/* compute_inds — replaces VectorQuantizerMS.compute_inds (models/mcq_vae.py:26-39),
+ * MultipleCodebookVectorQuantizer.compute_inds (:100-110) and the distance+argmin half of
+ * VectorQuantizer.forward (models/vq_vae.py:25-35).  `n_seg` input tensors of identical shape are
+ * processed in ONE launch (the x / y pair of CTMCQVAE.forward_action/_causal,
+ * models/ct_mcq_vae.py:530,536,555-556); pass n_seg = 1 otherwise. */
+int ctvq_argmin(const void* const* z_segs, int n_seg, const void* const* codebooks, int64_t B, int Dtot,
+                int HW, int C, int d, int K, int chan_stride, int dtype, int64_t* const* idx_out_segs,
+                void* workspace, size_t ws_bytes, int device, void* stream);
+
+/* compute_latents — replaces VectorQuantizerMS.compute_latents (models/mcq_vae.py:41-64) and
+ * MultipleCodebookVectorQuantizer.compute_latents (:112-127): gather by CALLER-SUPPLIED indices,
+ * loss_c = m*beta + m with m = mean((q - z)^2), straight-through output z + (q - z).
+ * loss_out has C+1 floats: per-codebook losses then their left-to-right sum (mcq_vae.py:125). */
+int ctvq_gather_st_loss(const void* z, const void* const* codebooks, const int64_t* idx, int64_t B,
+                        int Dtot, int HW, int C, int d, int K, int chan_stride, int dtype, float beta,
+                        void* q_out, float* loss_out, void* workspace, size_t ws_bytes, int device,
+                        void* stream);
+
+/* forward — replaces VectorQuantizer.forward (models/vq_vae.py:24-55), VectorQuantizerMS.forward
+ * (models/mcq_vae.py:67-74) and MultipleCodebookVectorQuantizer.forward (:130-137): argmin + gather +
+ * loss + straight-through in one pass over z (the N x K distance matrix never reaches HBM). */
+int ctvq_forward(const void* z, const void* const* codebooks, int64_t B, int Dtot, int HW, int C, int d,
+                 int K, int chan_stride, int dtype, float beta, int64_t* idx_out, void* q_out,
+                 float* loss_out, void* workspace, size_t ws_bytes, int device, void* stream);
+
+/* backward — replaces autograd through models/vq_vae.py:43-53:
+ *   gz[b,ch,p] = sum over (c,j) with c*chan_stride+j == ch of
+ *                g_out[b,c*d+j,p] + g_loss*beta*2*(z - q)/(N*d)          (zero where no slice reads ch)
+ *   gE[c,k,:]  = g_loss * 2/(N*d) * sum_{n: idx=k} (q_n - z_n)
+ * g_loss points to ONE device float (the gradient of the summed vq_loss); g_out may be NULL (treated as
+ * zero, e.g. the loss-only path).  gE_out [C,K,d] is overwritten (zeroed then accumulated). */
+int ctvq_backward(const void* z, const void* const* codebooks, const int64_t* idx, const void* g_out,
+                  const float* g_loss, int64_t B, int Dtot, int HW, int C, int d, int K, int chan_stride,
+                  int dtype, float beta, void* gz_out, float* gE_out, void* workspace, size_t ws_bytes,
+                  int device, void* stream);
+
+/* Gaussian branch — replaces VanillaVAE/BetaVAE.reparameterize (models/vanilla_vae.py:107-117,
+ * models/beta_vae.py:112-122) with eps supplied by the caller, fused with the KL term of
+ * loss_function (vanilla_vae.py:143, beta_vae.py:141): z = eps*exp(0.5*lv) + mu,
+ * kld = mean_b(-0.5 * sum_l(1 + lv - mu^2 - exp(lv))).  mu/logvar/eps/z are [B, L] fp32. */
+int ctvq_reparam_kld_fwd(const float* mu, const float* logvar, const float* eps, int64_t B, int L,
+                         float* z_out, float* kld_out, void* workspace, size_t ws_bytes, int device,
+                         void* stream);
+/* g_z [B,L] may be NULL; g_kld points to one device float (may be NULL = 0). */
+int ctvq_reparam_kld_bwd(const float* mu, const float* logvar, const float* eps, const float* g_z,
+                         const float* g_kld, int64_t B, int L, float* g_mu_out, float* g_logvar_out,
+                         int device, void* stream);
+
+/* Codebook-gradient all-reduce — the one collective of the path (replaces the share of Lightning's DDP
+ * bucket all-reduce that carries vq_layer.*.embedding.weight.grad, run.py:99).  NCCL is dlopen()ed from
+ * `libnccl_path` (the torch-bundled libnccl.so.2); communicators are created from a 128-byte unique id
+ * the caller broadcasts by its own means. */
+int ctvq_nccl_load(const char* libnccl_path);
+int ctvq_nccl_unique_id(void* id128_out);
+int ctvq_nccl_comm_init(void** comm_out, int nranks, int rank, const void* id128, int device);
+int ctvq_nccl_comm_destroy(void* comm);
+/* sum over ranks then multiply by `scale` (1/world = DDP's gradient averaging), in place, on `stream`. */
+int ctvq_allreduce_codebook_grad(void* comm, float* gE, size_t count, float scale, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTVQ_H_ */

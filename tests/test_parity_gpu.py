@@ -1,0 +1,324 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in modules) against
+  (1) the golden vectors minted from the live reference (tests/golden/*.npz),
+  (2) the plain-C oracle, which uses the kernels' evaluation order -> indices must match on EVERY row,
+  (3) the torch oracle (= the reference's ATen arithmetic) on larger seeded inputs -> mismatches only at
+      counted near-ties (relative gap < 1e-6, north_star),
+  (4) size-independent properties at benchmark sizes.
+Tolerances (north_star): indices bit-exact outside counted near-ties; losses / outputs / gradients within
+1e-5 relative in fp32.
+"""
+import pytest
+import torch
+
+from conftest import QUANT_GOLDENS, Golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def env():
+    import ct_vae_b200 as pkg
+    from ct_vae_b200 import _lib
+    from oracle import c_oracle, ctvq_oracle
+    assert torch.cuda.is_available()
+    _lib.lib()  # must load: there is no fallback
+    return pkg, _lib, ctvq_oracle, c_oracle
+
+
+def _build(pkg, g, dev):
+    if g.is_mcq:
+        c = len(g.codebooks)
+        k, d = g.codebooks[0].shape
+        m = pkg.MultipleCodebookVectorQuantizer(k, d * c, c, g.beta)
+        for q, e in zip(m.quantizers, g.codebooks):
+            q.embedding.weight.data.copy_(e)
+    else:
+        k, d = g.codebooks[0].shape
+        m = pkg.VectorQuantizerMS(k, d, g.beta)
+        m.embedding.weight.data.copy_(g.codebooks[0])
+    return m.to(dev)
+
+
+def _params(m):
+    return [p for p in m.parameters()]
+
+
+PATHS = ["simt", "tc"]
+
+
+def _select_path(_lib, path, m, z):
+    """Force a kernel path; skip when the tensor-core kernel does not cover the shape."""
+    _lib.set_path({"simt": _lib.PATH_SIMT, "tc": _lib.PATH_TC, "auto": _lib.PATH_AUTO}[path])
+
+
+@pytest.fixture(autouse=True)
+def _reset_path():
+    yield
+    try:
+        from ct_vae_b200 import _lib
+        _lib.set_path(_lib.PATH_AUTO)
+    except Exception:
+        pass
+
+
+def _run_forward(m, z, path, _lib):
+    _select_path(_lib, path, m, z)
+    try:
+        return m(z, inds=True)
+    except RuntimeError as e:
+        if path == "tc" and "unsupported" in str(e):
+            pytest.skip("shape not covered by the tcgen05 kernel")
+        raise
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name", QUANT_GOLDENS)
+def test_golden_forward_backward(env, name, path):
+    pkg, _lib, O, CO = env
+    g = Golden(name)
+    dev = torch.device("cuda:0")
+    m = _build(pkg, g, dev)
+    z = g["z"].to(dev).requires_grad_(True)
+    external = "external" in name
+    if external:
+        if path == "tc":
+            pytest.skip("gather by supplied indices has a single kernel")
+        out, loss = m.compute_latents(z, g["inds"].to(dev))
+        inds = g["inds"].to(dev)
+    else:
+        out, loss, inds = _run_forward(m, z, path, _lib)
+    torch.cuda.synchronize()
+    assert inds.dtype == torch.int64 and out.is_contiguous() and loss.dim() == 0
+    ref_inds = g["inds"].reshape(inds.shape)
+    # (2) kernel order == C-oracle order: exact on every row
+    if not external:
+        c_inds = CO.argmin(g["z"], g.codebooks).reshape(inds.shape)
+        assert torch.equal(inds.cpu(), c_inds), "indices differ from the C oracle (same evaluation order)"
+    # (1) vs the reference: only counted near-ties may differ
+    near = hard = 0
+    zc = g["z"]
+    for c, e in enumerate(g.codebooks):
+        d = e.shape[1]
+        ia = inds.cpu().reshape(zc.shape[0], len(g.codebooks), zc.shape[2], zc.shape[3])[:, c]
+        ib = ref_inds.reshape(zc.shape[0], len(g.codebooks), zc.shape[2], zc.shape[3])[:, c]
+        n, h = O.classify_index_mismatches(zc[:, c:c + d], e, ia, ib)
+        near, hard = near + n, hard + h
+    assert hard == 0, f"{hard} hard index mismatches vs the reference"
+    if near == 0:
+        assert torch.equal(out.detach().cpu(), g["out"]), "z + (q - z) is elementwise: bit-exact given equal indices"
+    assert rel_err(loss.detach().cpu(), g["loss"]) < TOL
+    if "g_out" in g:
+        (out * g["g_out"].to(dev)).sum().add(float(g["g_loss"]) * loss).backward()
+        torch.cuda.synchronize()
+        if near == 0:
+            assert rel_err(z.grad.cpu(), g["gz"]) < TOL
+            for p, ref in zip(_params(m), g.grad_codebooks):
+                assert rel_err(p.grad.cpu(), ref) < TOL
+    print(f"{name}[{path}]: near-tie index mismatches vs reference: {near}")
+
+
+@pytest.mark.parametrize("name", ["mcq_cfg2_trained", "vq_cfg1_trained", "edge_odd", "edge_mcq_odd"])
+def test_compute_inds_and_compute_latents_split(env, name):
+    """models/mcq_vae.py:67-74: forward == compute_inds -> compute_latents."""
+    pkg, _lib, O, CO = env
+    g = Golden(name)
+    dev = torch.device("cuda:0")
+    m = _build(pkg, g, dev)
+    z = g["z"].to(dev)
+    with torch.no_grad():
+        out, loss, inds = m(z, inds=True)
+        inds2 = m.compute_inds(z)
+        out2, loss2 = m.compute_latents(z, inds2)
+    assert torch.equal(inds, inds2)
+    assert torch.equal(out, out2)
+    assert rel_err(loss2.cpu(), loss.cpu()) < 1e-6
+
+
+def test_pair_batching_matches_two_calls(env):
+    """CT pair (models/ct_mcq_vae.py:530,536): x and y in one launch == two launches."""
+    pkg, _lib, O, CO = env
+    g = Golden("ct_cfg3_trained")
+    dev = torch.device("cuda:0")
+    m = _build(pkg, g, dev)
+    x = g["z"].to(dev)
+    y = torch.roll(x, 3, 0) * 1.25
+    ix, iy = m.compute_inds_pair(x, y)
+    assert torch.equal(ix, m.compute_inds(x)) and torch.equal(iy, m.compute_inds(y))
+    assert torch.equal(ix.cpu(), g["inds"].reshape(ix.shape)) or True  # near-ties allowed, checked elsewhere
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("cfg", [
+    # (name, B, D, H, W, C, K, codebook) — sizes the CPU oracle finishes in seconds
+    ("cfg1_init", 64, 64, 16, 16, 1, 512, "init"),       # configs/vq_vae.yaml: N=16384, the tie-heavy case
+    ("cfg1_trained", 64, 64, 16, 16, 1, 512, "trained"),
+    ("cfg2_init", 64, 128, 8, 8, 4, 64, "init"),          # configs/mcq_vae.yaml
+    ("cfg2_trained", 256, 128, 8, 8, 4, 64, "trained"),
+    ("cfg3_trained", 32, 128, 8, 8, 1, 64, "trained"),    # configs/ct_mcq_vae.yaml (x and y)
+    ("sweep_d32_k256", 256, 32, 16, 16, 1, 256, "trained"),
+    ("sweep_d128_k1024", 64, 128, 16, 16, 1, 1024, "trained"),
+    ("sweep_d256_k256", 16, 256, 16, 16, 1, 256, "init"),
+    ("ragged_hw49_d24", 37, 24, 7, 7, 3, 50, "trained"),
+])
+def test_seeded_vs_oracles(env, cfg, path):
+    pkg, _lib, O, CO = env
+    name, B, D, H, W, C, K, kind = cfg
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1234)
+    d = D // C
+    if C == 1:
+        m = pkg.VectorQuantizerMS(K, D, 0.25)
+        books = [m.embedding.weight]
+    else:
+        m = pkg.MultipleCodebookVectorQuantizer(K, D, C, 0.25)
+        books = [q.embedding.weight for q in m.quantizers]
+    if kind == "trained":
+        for e in books:
+            e.data = torch.randn(K, d) * 0.5
+    z_cpu = torch.randn(B, D, H, W)
+    m = m.to(dev)
+    z = z_cpu.to(dev).requires_grad_(True)
+    out, loss, inds = _run_forward(m, z, path, _lib)
+    g_out = torch.randn(B, C * d, H, W)
+    (out * g_out.to(dev)).sum().add(0.7 * loss).backward()
+    torch.cuda.synchronize()
+    books_cpu = [e.detach().cpu() for e in books]
+    inds_cpu = inds.cpu().reshape(B, C, H, W)
+    # C oracle: same evaluation order -> exact
+    assert torch.equal(inds_cpu, CO.argmin(z_cpu, books_cpu)), "indices differ from the C oracle"
+    # torch oracle (= reference ATen arithmetic): near-ties only
+    ref_inds = O.mcq_compute_inds(z_cpu, books_cpu)
+    near = hard = 0
+    for c, e in enumerate(books_cpu):
+        n, h = O.classify_index_mismatches(z_cpu[:, c:c + d], e, inds_cpu[:, c], ref_inds[:, c])
+        near, hard = near + n, hard + h
+    assert hard == 0
+    # outputs / loss / grads of the oracle evaluated at OUR indices (so near-ties do not blur the check)
+    ref_out, ref_loss, _ = O.mcq_compute_latents(z_cpu, inds_cpu, books_cpu, 0.25)
+    assert torch.equal(out.detach().cpu(), ref_out)
+    assert rel_err(loss.detach().cpu(), ref_loss) < TOL
+    gz, ges = O.mcq_backward(z_cpu, inds_cpu, books_cpu, 0.25, g_out, torch.tensor(0.7))
+    assert rel_err(z.grad.cpu(), gz) < TOL
+    for e, ref in zip(books, ges):
+        assert rel_err(e.grad.cpu(), ref) < TOL
+    print(f"{name}[{path}]: rows={B * H * W * C} near-tie mismatches vs reference arithmetic: {near}")
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_full_size_properties(env, path):
+    """Benchmark-size input (N = 1M rows, C=4, K=64): properties that need no CPU oracle."""
+    pkg, _lib, O, CO = env
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    B, D, H, W, C, K = 16384, 128, 8, 8, 4, 64
+    d = D // C
+    m = pkg.MultipleCodebookVectorQuantizer(K, D, C, 0.25).to(dev)
+    for q in m.quantizers:
+        q.embedding.weight.data = torch.randn(K, d, device=dev) * 0.5
+    z = torch.randn(B, D, H, W, device=dev)
+    with torch.no_grad():
+        out, loss, inds = _run_forward(m, z, path, _lib)
+        assert int(inds.min()) >= 0 and int(inds.max()) < K
+        # (a) out - z == E[idx] - z  (straight-through identity), checked through an independent torch gather
+        total = torch.zeros((), device=dev, dtype=torch.float64)
+        for c, q in enumerate(m.quantizers):
+            e = q.embedding.weight
+            zc = z[:, c:c + d].permute(0, 2, 3, 1)
+            qc = e[inds[:, c]]
+            exp = zc + (qc - zc)
+            assert torch.equal(out[:, c * d:(c + 1) * d].permute(0, 2, 3, 1), exp)
+            mse = ((qc - zc).double() ** 2).mean()
+            total += mse * 0.25 + mse
+            # (b) optimality: the chosen code is at least as close as 8 random other codes (fp64 distances)
+            rnd = torch.randint(0, K, (8,), device=dev)
+            dsel = ((qc - zc).double() ** 2).sum(-1)
+            for r in rnd:
+                dr = ((e[r] - zc).double() ** 2).sum(-1)
+                assert bool((dsel <= dr + 1e-6 * (dr.abs() + 1)).all())
+        assert abs(float(loss) - float(total)) < TOL * abs(float(total))
+        # (c) idempotence: quantising the codewords themselves returns the same codes at zero loss
+        zq = torch.cat([q.embedding.weight[inds[:, c]].permute(0, 3, 1, 2) for c, q in enumerate(m.quantizers)], 1)
+        if C == 1 or m.chan_stride == d:
+            out2, loss2, inds2 = m(zq, inds=True)
+            assert torch.equal(inds2, inds)
+
+
+def test_reparam_kld_golden(env):
+    pkg, _lib, O, CO = env
+    from ct_vae_b200 import gaussian
+    g = Golden("reparam_kld")
+    dev = torch.device("cuda:0")
+    mu = g["mu"].to(dev).requires_grad_(True)
+    lv = g["logvar"].to(dev).requires_grad_(True)
+    z, kld = gaussian.reparam_kld(mu, lv, g["eps"].to(dev))
+    assert rel_err(z.detach().cpu(), g["z"]) < TOL
+    assert rel_err(kld.detach().cpu(), g["kld"]) < TOL
+    ((z * g["g_z"].to(dev)).sum() + float(g["g_kld"]) * kld).backward()
+    assert rel_err(mu.grad.cpu(), g["g_mu"]) < TOL
+    assert rel_err(lv.grad.cpu(), g["g_logvar"]) < TOL
+
+
+def test_reparam_kld_cfg5_shape_and_rng_stream(env):
+    """configs/vae.yaml latent_dim=128, batch 4096: eps=None must consume the generator like randn_like(std)."""
+    pkg, _lib, O, CO = env
+    from ct_vae_b200 import gaussian
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1265)
+    mu = torch.randn(4096, 128, device=dev)
+    lv = torch.randn(4096, 128, device=dev) * 0.5
+    torch.manual_seed(7)
+    z, kld = gaussian.reparam_kld(mu, lv)
+    torch.manual_seed(7)
+    eps = torch.randn_like(torch.exp(0.5 * lv))
+    ref_z = O.reparameterize(mu.cpu(), lv.cpu(), eps.cpu())
+    assert rel_err(z.cpu(), ref_z) < TOL
+    assert rel_err(kld.cpu(), O.kld(mu.cpu(), lv.cpu())) < TOL
+
+
+def test_cuda_graph_capture_forward_backward(env):
+    """No host syncs / allocations-by-the-library on the path: a whole fwd+bwd replays from a CUDA graph."""
+    pkg, _lib, O, CO = env
+    g = Golden("mcq_cfg2_trained")
+    dev = torch.device("cuda:0")
+    m = _build(pkg, g, dev)
+    z = g["z"].to(dev).requires_grad_(True)
+    g_out = g["g_out"].to(dev)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            out, loss = m(z)
+            (out * g_out).sum().add(0.7 * loss).backward()
+            z.grad = None
+            m.zero_grad(set_to_none=True)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out, loss = m(z)
+        (out * g_out).sum().add(0.7 * loss).backward()
+    z.data.copy_(g["z"].to(dev))
+    graph.replay()
+    torch.cuda.synchronize()
+    assert rel_err(loss.detach().cpu(), g["loss"]) < TOL
+    assert rel_err(z.grad.cpu(), g["gz"]) < TOL
+    graph.replay()
+    torch.cuda.synchronize()
+    assert rel_err(loss.detach().cpu(), g["loss"]) < TOL, "workspace must be self-cleaning across replays"
+
+
+def test_bad_indices_are_flagged_not_fatal(env):
+    pkg, _lib, O, CO = env
+    dev = torch.device("cuda:0")
+    m = pkg.VectorQuantizerMS(8, 4).to(dev)
+    z = torch.randn(2, 4, 3, 3, device=dev)
+    with pytest.raises(RuntimeError):
+        m.compute_latents(z, torch.zeros(5, dtype=torch.int64, device=dev))  # wrong element count
+
+
+def test_cpu_tensor_raises(env):
+    pkg, _lib, O, CO = env
+    m = pkg.VectorQuantizer(8, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(2, 4, 3, 3))
