@@ -1,0 +1,84 @@
+"""Benchmark harness pieces that sit AROUND the hot path (not part of it): a stand-in for the MCQ-VAE model
+shell and for the Lightning training step, needed because neither the reference tree nor pytorch_lightning
+exists on the GPU box.
+
+* ``MCQVAEShell`` has the layer structure of models/mcq_vae.py:142-317 (stride-2 4x4 conv encoder, 3x3 conv,
+  six residual layers, 1x1 conv to the embedding dimension; mirrored decoder with transposed convs and tanh)
+  built from stock torch.nn layers — cuDNN stays the conv engine, exactly as in the reference — with the
+  drop-in ``MultipleCodebookVectorQuantizer`` as ``vq_layer``.  forward/loss_function keep the reference's
+  return conventions (mcq_vae.py:262-284).
+* ``train_step`` is the body of experiment.py:44-59 plus the optimiser step Lightning performs
+  (Adam, experiment.py:158-160).
+"""
+from typing import List, Optional
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .modules import MultipleCodebookVectorQuantizer
+
+
+class _Residual(nn.Module):  # models/vq_vae.py:57-70
+    def __init__(self, ch: int):
+        super().__init__()
+        self.resblock = nn.Sequential(nn.Conv2d(ch, ch, 3, padding=1, bias=False), nn.ReLU(True),
+                                      nn.Conv2d(ch, ch, 1, bias=False))
+
+    def forward(self, x):
+        return x + self.resblock(x)
+
+
+def _act(conv):
+    return nn.Sequential(conv, nn.LeakyReLU())
+
+
+class MCQVAEShell(nn.Module):
+    def __init__(self, in_channels: int = 3, embedding_dim: int = 128, num_embeddings: int = 64,
+                 hidden_dims: Optional[List[int]] = None, beta: float = 0.25, img_size: int = 64, codebooks: int = 4):
+        super().__init__()
+        hidden = list(hidden_dims) if hidden_dims is not None else [128, 256]
+        self.embedding_dim, self.num_embeddings, self.img_size = embedding_dim, num_embeddings, img_size
+        enc, ch = [], in_channels
+        for h in hidden:
+            enc.append(_act(nn.Conv2d(ch, h, 4, stride=2, padding=1)))
+            ch = h
+        enc.append(_act(nn.Conv2d(ch, ch, 3, padding=1)))
+        enc += [_Residual(ch) for _ in range(6)]
+        enc.append(nn.LeakyReLU())
+        enc.append(_act(nn.Conv2d(ch, embedding_dim, 1)))
+        self.encoder = nn.Sequential(*enc)
+        self.vq_layer = MultipleCodebookVectorQuantizer(num_embeddings, embedding_dim, codebooks, beta)
+        dec = [_act(nn.Conv2d(embedding_dim, hidden[-1], 3, padding=1))]
+        dec += [_Residual(hidden[-1]) for _ in range(6)]
+        dec.append(nn.LeakyReLU())
+        rev = hidden[::-1]
+        for a, b in zip(rev, rev[1:]):
+            dec.append(_act(nn.ConvTranspose2d(a, b, 4, stride=2, padding=1)))
+        dec.append(nn.Sequential(nn.ConvTranspose2d(rev[-1], in_channels, 4, stride=2, padding=1), nn.Tanh()))
+        self.decoder = nn.Sequential(*dec)
+
+    def encode(self, x):
+        return [self.encoder(x)]
+
+    def decode(self, z):
+        return self.decoder(z)
+
+    def forward(self, x, **kwargs):
+        q, vq_loss = self.vq_layer(self.encode(x)[0])
+        return [self.decode(q), x, vq_loss]
+
+    def loss_function(self, *args, **kwargs) -> dict:
+        recons, inp, vq_loss = args[0], args[1], args[2]
+        recons_loss = F.mse_loss(recons, inp)
+        return {"loss": recons_loss + vq_loss, "Reconstruction_Loss": recons_loss, "VQ_Loss": vq_loss}
+
+
+def train_step(model: nn.Module, optimizer: torch.optim.Optimizer, images: torch.Tensor, m_n: float = 0.00025):
+    """experiment.py:44-59 (+ Lightning's zero_grad/backward/step).  Returns the loss tensor (no host sync)."""
+    optimizer.zero_grad(set_to_none=True)
+    results = model(images)
+    losses = model.loss_function(*results, M_N=m_n)
+    losses["loss"].backward()
+    optimizer.step()
+    return losses["loss"]
