@@ -418,6 +418,10 @@ int launch_backward(const BwdParams& p0, cudaStream_t s) {
     BwdParams p = p0;
     cudaError_t e = cudaMemsetAsync(p.gE, 0, sizeof(float) * (size_t)p.C * p.K * p.d, s);
     if (e != cudaSuccess) return (int)e;
+    {
+        const int rc = launch_backward_tiled(p, s);  // shared-memory accumulator, no atomics in the inner loop
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
+    }
     const bool vec = (p.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.z) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.gz) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.idx) & 15) == 0) &&
                      (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 15) == 0);
