@@ -74,5 +74,6 @@ int launch_reparam_bwd(const float* mu, const float* lv, const float* eps, const
                        long long B, int L, float* g_mu, float* g_lv, cudaStream_t s);
 int launch_forward_tc(const QuantParams& p, cudaStream_t s);  // returns CTVQ_E_UNSUPPORTED when shape not covered
 bool tc_supported(const QuantParams& p);
+int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s);  // shape-specialised tcgen05 kernels
 
 }  // namespace ctvq

@@ -1,0 +1,372 @@
+// Shape-specialised tcgen05 forward kernel: same algorithm as ctvq_tc.cu (tf32 distance GEMM in TMEM, rigorous
+// candidate filter, exact fp32 re-scoring, fused gather/straight-through/loss) with every inner loop unrolled
+// against compile-time D (channels per codebook), NK (padded codes per codebook) and HW, so shared-memory and
+// global addresses are immediates and the epilogue is ~4 instructions per (row, code):
+//     pass 1   a_k = fma(-2, dot_k, |e_k|^2)  and a 4-way min tree            (FFMA + FMNMX)
+//     pass 2   survivor bitmask  a_k <= min + bound                           (FSETP + predicated LOP)
+// Two warpgroups (8 warps) per CTA split the codebooks by parity; 2 CTAs per SM share the 512 TMEM columns, so
+// one CTA's TMA + MMA latency hides behind the other's epilogue.
+// Replaces models/vq_vae.py:30-55 / models/mcq_vae.py:26-64,100-127 for the configs' shapes.
+#include "ctvq_tc_ptx.cuh"
+
+namespace ctvq {
+using namespace tc;
+namespace {
+
+constexpr int kFT = 256;  // threads: 2 warpgroups x 4 warps (warp & 3 selects the TMEM lane quarter)
+
+__device__ __forceinline__ void tmem_ld64(uint32_t addr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(addr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct FastParams {
+    QuantParams q;
+    int ntiles;
+};
+
+// D: channels per codebook, NK: codes per codebook padded to a multiple of 64 (<= 256), HWT: H*W,
+// CPW: codebooks per warpgroup (C <= 2*CPW, C*NK <= 256)
+template <int D, int NK, int HWT, int CPW>
+__global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams P, const __grid_constant__ Maps maps) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const QuantParams& p = P.q;
+    const int C = p.C, K = p.K;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quarter = warp & 3, wg = warp >> 2;
+    constexpr int DJB = (D + 31) / 32;
+    constexpr uint32_t kSlab = 4u * D * 128u;        // one codebook's A slab: 4 row blocks x [D][128 B]
+    constexpr uint32_t kEcb = (uint32_t)DJB * NK * 128u;
+    uint8_t* a_s = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* e_s = a_s + (size_t)C * kSlab;
+    float* ee_s = reinterpret_cast<float*>(e_s + (size_t)C * kEcb);  // [C][NK]
+    float* emax_s = ee_s + C * NK;                                   // [C] (+pad)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(emax_s + ((C + 3) & ~3));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const uint32_t a_base = smem_u32(a_s), e_base = smem_u32(e_s);
+    const uint32_t bar_a = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1]);
+
+    if (tid == 0) {
+        mbar_init(bar_a, 1);
+        mbar_init(bar_m, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+    // ---- codebooks -> K-major SWIZZLE_128B tiles (once per persistent CTA) + |e|^2 ----------------------------
+    for (int i = tid; i < C * NK * DJB * 32; i += kFT) {
+        const int j = i % (DJB * 32), ck = i / (DJB * 32), k = ck % NK, c = ck / NK;
+        const float v = (k < K && j < D) ? __ldg(p.E[c] + (size_t)k * D + j) : 0.0f;
+        *reinterpret_cast<float*>(e_s + (size_t)c * kEcb + e_off(k, j, NK)) = v;
+    }
+    for (int i = tid; i < C * NK; i += kFT) {
+        const int k = i % NK, c = i / NK;
+        float a = CUDART_INF_F;
+        if (k < K) {
+            a = 0.0f;
+            const float* row = p.E[c] + (size_t)k * D;
+#pragma unroll 8
+            for (int j = 0; j < D; ++j) { const float v = __ldg(row + j); a = fmaf(v, v, a); }
+        }
+        ee_s[i] = a;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid < C) {
+        float mx = 0.0f;
+        for (int k = 0; k < K; ++k) mx = fmaxf(mx, ee_s[tid * NK + k]);
+        emax_s[tid] = sqrtf(mx) * 1.0001f;
+    }
+    const uint32_t tmem_base = *tmem_slot;
+    __syncthreads();
+
+    // lane-dependent pieces of the swizzled addresses
+    uint32_t zsw[4];  // byte offset of (this lane's row, channel j) inside a row block, minus j*128, for j & 3 = x
+#pragma unroll
+    for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ x) & 3) << 5) + ((lane & 7) << 2);
+
+    uint32_t phase_a = 0, phase_m = 0;
+    float lsum[CPW];
+#pragma unroll
+    for (int ci = 0; ci < CPW; ++ci) lsum[ci] = 0.0f;
+
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const int seg = tile / p.tiles_per_seg;
+        const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
+        const long long n = row0 + quarter * 32 + lane;
+        const bool valid = n < p.N;  // warp-uniform (N is a multiple of 32)
+        const long long b = n / HWT;
+        const int hw = (int)(n - b * HWT);
+        if (tid == 0) {
+            int nblk = 0;
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) nblk += (row0 + 32 * mb < p.N) ? 1 : 0;
+            mbar_expect_tx(bar_a, (uint32_t)(C * nblk) * D * 128u);
+            for (int c = 0; c < C; ++c)
+                for (int mb = 0; mb < nblk; ++mb) {
+                    const long long nb = row0 + 32 * mb;
+                    const long long bb = nb / HWT;
+                    tma_load_3d(a_base + c * kSlab + mb * D * 128u, &maps.m[seg], bar_a, (int)(nb - bb * HWT), c * p.cs,
+                                (int)bb);
+                }
+        }
+        mbar_wait(bar_a, phase_a);
+        phase_a ^= 1;
+        tc_fence_after();
+        if (tid == 0) {
+            const uint32_t idesc = instr_desc_tf32(NK);
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int s = 0; s < D / 8; ++s) {
+                    const uint64_t ad = smem_desc(a_base + c * kSlab + s * 1024u, D * 128u, 512u, 1u);
+                    const uint64_t bd = smem_desc(e_base + c * kEcb + (s >> 2) * NK * 128u + (s & 3) * 32u, 16u, 1024u, 2u);
+                    umma_tf32(tmem_base + c * NK, ad, bd, idesc, s > 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(bar_m);
+        }
+        // |z|^2 of this thread's row for its codebooks while the tensor core works (exact sequential chains)
+        float zz[CPW];
+        if (valid) {
+#pragma unroll
+            for (int ci = 0; ci < CPW; ++ci) zz[ci] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+#pragma unroll
+                for (int ci = 0; ci < CPW; ++ci) {
+                    const int c = wg + 2 * ci;
+                    if (c < C) {
+                        const float v = *reinterpret_cast<const float*>(a_s + c * kSlab + quarter * (D * 128u) + j * 128 + zsw[j & 3]);
+                        zz[ci] = fmaf(v, v, zz[ci]);
+                    }
+                }
+            }
+        }
+        mbar_wait(bar_m, phase_m);
+        phase_m ^= 1;
+        tc_fence_after();
+
+        if (valid) {
+#pragma unroll
+            for (int ci = 0; ci < CPW; ++ci) {
+                const int c = wg + 2 * ci;
+                if (c >= C) continue;
+                const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + c * NK;
+                const float* ee = ee_s + c * NK;
+                const uint8_t* zrow = a_s + c * kSlab + quarter * (D * 128u);
+                const uint8_t* ecb = e_s + (size_t)c * kEcb;
+                constexpr int NCH = NK / 64;
+                float a[64];
+                // ---- pass 1: approximate distances (without |z|^2) and their minimum --------------------------------
+                float m0 = CUDART_INF_F, m1 = CUDART_INF_F, m2 = CUDART_INF_F, m3 = CUDART_INF_F;
+#pragma unroll
+                for (int chn = 0; chn < NCH; ++chn) {
+                    tmem_ld64(trow + chn * 64, a);
+#pragma unroll
+                    for (int i = 0; i < 64; i += 4) {
+                        const float4 e4 = *reinterpret_cast<const float4*>(ee + chn * 64 + i);
+                        a[i] = fmaf(-2.0f, a[i], e4.x);
+                        a[i + 1] = fmaf(-2.0f, a[i + 1], e4.y);
+                        a[i + 2] = fmaf(-2.0f, a[i + 2], e4.z);
+                        a[i + 3] = fmaf(-2.0f, a[i + 3], e4.w);
+                        m0 = fminf(m0, a[i]); m1 = fminf(m1, a[i + 1]); m2 = fminf(m2, a[i + 2]); m3 = fminf(m3, a[i + 3]);
+                    }
+                }
+                const float mn = fminf(fminf(m0, m1), fminf(m2, m3));
+                // rigorous bound on |tf32 distance - exact-chain distance|
+                const float emax = emax_s[c];
+                const float zzc = zz[ci];
+                const float thr = 2.0f * (0.00390625f * sqrtf(zzc) * 1.0001f * emax + 9.5367431640625e-7f * (zzc + emax * emax));
+                const float lim = mn + thr;
+                // ---- pass 2: survivors as a bitmask ------------------------------------------------------------------------
+                unsigned mask[NCH * 2];
+                int cnt = 0;
+#pragma unroll
+                for (int chn = 0; chn < NCH; ++chn) {
+                    if (NCH > 1) {
+                        tmem_ld64(trow + chn * 64, a);
+#pragma unroll
+                        for (int i = 0; i < 64; i += 4) {
+                            const float4 e4 = *reinterpret_cast<const float4*>(ee + chn * 64 + i);
+                            a[i] = fmaf(-2.0f, a[i], e4.x);
+                            a[i + 1] = fmaf(-2.0f, a[i + 1], e4.y);
+                            a[i + 2] = fmaf(-2.0f, a[i + 2], e4.z);
+                            a[i + 3] = fmaf(-2.0f, a[i + 3], e4.w);
+                        }
+                    }
+                    unsigned lo = 0u, hi = 0u;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (a[i] <= lim) lo |= 1u << i;
+                        if (a[32 + i] <= lim) hi |= 1u << i;
+                    }
+                    mask[2 * chn] = lo;
+                    mask[2 * chn + 1] = hi;
+                    cnt += __popc(lo) + __popc(hi);
+                }
+                // ---- decide ---------------------------------------------------------------------------------------------------
+                int bi = 0;
+                const bool finite = (zzc < CUDART_INF_F) && (mn > -CUDART_INF_F) && (mn < CUDART_INF_F) && cnt >= 1;
+                if (finite && cnt == 1) {
+#pragma unroll
+                    for (int w = 0; w < NCH * 2; ++w)
+                        if (mask[w]) bi = w * 32 + __ffs(mask[w]) - 1;
+                } else {
+                    float bv = CUDART_INF_F;
+                    bi = 0x7fffffff;
+                    if (!finite) {
+                        // non-finite row: exact scan of every code with torch.argmin's NaN rule
+                        for (int k = 0; k < K; ++k) {
+                            const uint8_t* erow = ecb + k * 128;
+                            float dot = 0.0f;
+#pragma unroll
+                            for (int j = 0; j < D; ++j)
+                                dot = fmaf(*reinterpret_cast<const float*>(zrow + j * 128 + zsw[j & 3]),
+                                           *reinterpret_cast<const float*>(erow + (j >> 5) * NK * 128 +
+                                                                           (((((j & 31) >> 2) ^ (k & 7)) & 7) << 4) + ((j & 3) << 2)), dot);
+                            const float dist = dist_f32(zzc, ee[k], dot);
+                            if (!(dist >= bv) && (bv == bv)) { bv = dist; bi = k; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < NCH * 2; ++w) {
+                            unsigned mk = mask[w];
+                            while (mk) {
+                                const int k = w * 32 + __ffs(mk) - 1;
+                                mk &= mk - 1;
+                                const uint8_t* erow = ecb + k * 128;
+                                const uint32_t kx = (uint32_t)(k & 7) << 4;
+                                float dot = 0.0f;
+#pragma unroll
+                                for (int j = 0; j < D; j += 4) {
+                                    const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 +
+                                                                                       ((((j & 31) >> 2) << 4) ^ kx));
+                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + j * 128 + zsw[j & 3]), e4.x, dot);
+                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + (j + 1) * 128 + zsw[(j + 1) & 3]), e4.y, dot);
+                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + (j + 2) * 128 + zsw[(j + 2) & 3]), e4.z, dot);
+                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + (j + 3) * 128 + zsw[(j + 3) & 3]), e4.w, dot);
+                                }
+                                const float dist = dist_f32(zzc, ee[k], dot);
+                                if (dist < bv) { bv = dist; bi = k; }  // ascending k: strict '<' keeps the first minimum
+                            }
+                        }
+                    }
+                }
+                p.idx[seg][((size_t)b * C + c) * HWT + hw] = (long long)bi;
+                // ---- fused gather + straight-through + loss ------------------------------------------------------------------
+                if (p.fused) {
+                    float* out = p.q + ((size_t)b * C * D + (size_t)c * D) * HWT + hw;
+                    const uint8_t* erow = ecb + bi * 128;
+                    const uint32_t kx = (uint32_t)(bi & 7) << 4;
+                    float ls0 = 0.0f, ls1 = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < D; j += 4) {
+                        const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 + ((((j & 31) >> 2) << 4) ^ kx));
+                        const float z0 = *reinterpret_cast<const float*>(zrow + j * 128 + zsw[j & 3]);
+                        const float z1 = *reinterpret_cast<const float*>(zrow + (j + 1) * 128 + zsw[(j + 1) & 3]);
+                        const float z2 = *reinterpret_cast<const float*>(zrow + (j + 2) * 128 + zsw[(j + 2) & 3]);
+                        const float z3 = *reinterpret_cast<const float*>(zrow + (j + 3) * 128 + zsw[(j + 3) & 3]);
+                        const float d0 = __fsub_rn(e4.x, z0), d1 = __fsub_rn(e4.y, z1);
+                        const float d2 = __fsub_rn(e4.z, z2), d3 = __fsub_rn(e4.w, z3);
+                        out[(size_t)j * HWT] = __fadd_rn(z0, d0);  // z + (q - z), models/vq_vae.py:53
+                        out[(size_t)(j + 1) * HWT] = __fadd_rn(z1, d1);
+                        out[(size_t)(j + 2) * HWT] = __fadd_rn(z2, d2);
+                        out[(size_t)(j + 3) * HWT] = __fadd_rn(z3, d3);
+                        ls0 = fmaf(d0, d0, ls0); ls1 = fmaf(d1, d1, ls1);
+                        ls0 = fmaf(d2, d2, ls0); ls1 = fmaf(d3, d3, ls1);
+                    }
+                    lsum[ci] += ls0 + ls1;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // TMEM columns and the A slabs are free again
+    }
+    // ---- loss: warp sums -> fp64 atomics -> last CTA finalises -----------------------------------------------------
+    if (p.fused) {
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+            const int c = wg + 2 * ci;
+            double v = (double)lsum[ci];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && c < C) atomicAdd(&p.loss_acc[c], v);
+        }
+        __shared__ unsigned s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1u);
+        __syncthreads();
+        if (s_last && tid == 0) {
+            __threadfence();
+            float total = 0.0f;
+            const double denom = (double)p.N * (double)D;
+            for (int c = 0; c < C; ++c) {
+                const float m = (float)(__ldcg(&p.loss_acc[c]) / denom);
+                const float l = __fadd_rn(__fmul_rn(m, p.beta), m);
+                p.loss_out[c] = l;
+                total = __fadd_rn(total, l);
+                p.loss_acc[c] = 0.0;
+            }
+            p.loss_out[C] = total;
+            *p.ticket = 0u;
+            __threadfence();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+template <int D, int NK, int HWT, int CPW>
+int launch_fast(const QuantParams& p0, cudaStream_t s) {
+    FastParams P;
+    P.q = p0;
+    P.q.tiles_per_seg = (int)((p0.N + kTM - 1) / kTM);
+    P.ntiles = P.q.tiles_per_seg * p0.n_seg;
+    Maps maps;
+    if (make_maps(p0, maps) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
+    constexpr int DJB = (D + 31) / 32;
+    const size_t smem = (size_t)p0.C * 4 * D * 128 + (size_t)p0.C * DJB * NK * 128 +
+                        sizeof(float) * ((size_t)p0.C * NK + ((p0.C + 3) & ~3)) + 2 * 8 + 16 + 1024;
+    if (smem > 113 * 1024) return CTVQ_E_UNSUPPORTED;
+    auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, CPW>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int grid = 148 * 2;
+    if (grid > P.ntiles) grid = P.ntiles;
+    kern<<<grid, kFT, smem, s>>>(P, maps);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// Shapes with a specialised kernel; anything else falls through to the generic tcgen05 kernel / SIMT.
+int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
+    if (p.HW % 32 != 0 || p.K > 64 || p.C > 4) return CTVQ_E_UNSUPPORTED;
+    for (int sg = 0; sg < p.n_seg; ++sg)
+        if (reinterpret_cast<uintptr_t>(p.z[sg]) & 15) return CTVQ_E_UNSUPPORTED;
+    if (!encode_fn()) return CTVQ_E_UNSUPPORTED;
+    if (p.d == 32 && p.HW == 64 && p.C <= 4) return p.C <= 2 ? launch_fast<32, 64, 64, 1>(p, s) : launch_fast<32, 64, 64, 2>(p, s);
+    if (p.d == 128 && p.HW == 64 && p.C == 1) return launch_fast<128, 64, 64, 1>(p, s);
+    return CTVQ_E_UNSUPPORTED;
+}
+
+}  // namespace ctvq
