@@ -419,7 +419,9 @@ int launch_backward(const BwdParams& p0, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(p.gE, 0, sizeof(float) * (size_t)p.C * p.K * p.d, s);
     if (e != cudaSuccess) return (int)e;
     {
-        const int rc = launch_backward_tiled(p, s);  // shared-memory accumulator, no atomics in the inner loop
+        int rc = launch_backward_fast(p, s);  // shape-specialised (configs' shapes)
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
+        rc = launch_backward_tiled(p, s);     // shared-memory accumulator, no atomics in the inner loop
         if (rc != CTVQ_E_UNSUPPORTED) return rc;
     }
     const bool vec = (p.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.z) & 15) == 0) &&
