@@ -345,12 +345,12 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int make_maps(const QuantParams& p0, Maps& maps) {
+int make_maps(const QuantParams& p0, Maps& maps, int box_channels) {
     if (!encode_fn()) return CTVQ_E_UNSUPPORTED;
     for (int sg = 0; sg < p0.n_seg; ++sg) {
         const cuuint64_t dims[3] = {(cuuint64_t)p0.HW, (cuuint64_t)p0.Dtot, (cuuint64_t)p0.B};
         const cuuint64_t strides[2] = {(cuuint64_t)p0.HW * 4, (cuuint64_t)p0.HW * p0.Dtot * 4};
-        const cuuint32_t box[3] = {32u, (cuuint32_t)p0.d, 1u};
+        const cuuint32_t box[3] = {32u, (cuuint32_t)(box_channels > 0 ? box_channels : p0.d), 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         const CUresult r = encode_fn()(&maps.m[sg], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p0.z[sg]), dims,
                                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -385,7 +385,7 @@ int launch_forward_tc(const QuantParams& p0, cudaStream_t s) {
     P.e_bytes = (unsigned)pl.e_bytes;
     P.dbg = g_dbg;
     Maps maps;
-    if (make_maps(p0, maps) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
+    if (make_maps(p0, maps, 0) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(vq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return (int)e;
     int grid = 148 * pl.per_sm;

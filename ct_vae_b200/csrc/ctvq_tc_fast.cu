@@ -42,32 +42,63 @@ struct FastParams {
     int ntiles;
 };
 
-// D: channels per codebook, NK: codes per codebook padded to a multiple of 64 (<= 256), HWT: H*W,
-// CPW: codebooks per warpgroup (C <= 2*CPW, C*NK <= 256)
-template <int D, int NK, int HWT, int CPW>
+__device__ __forceinline__ void or_if_le(unsigned& m, float a, float lim, unsigned bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(a), "f"(lim), "r"(bit));
+}
+
+// D: channels per codebook; NK: codes per codebook padded to a multiple of 64; HWT: H*W; C: codebooks (C*NK <= 256);
+// CS: channel stride between codebook slices (1 = the reference's overlapping slices); NSTAGE: TMA ring depth.
+// ONE shared-memory slab of USEDP = round8((C-1)*CS + D) channels per row block serves every codebook: codebook c's
+// UMMA descriptors simply start c*CS rows (128 B each) into it.
+template <int D, int NK, int HWT, int C, int CS, int NSTAGE>
 __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams P, const __grid_constant__ Maps maps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const QuantParams& p = P.q;
-    const int C = p.C, K = p.K;
+    const int K = p.K;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quarter = warp & 3, wg = warp >> 2;
+    constexpr int CPW = (C + 1) / 2;               // codebooks per warpgroup (split by parity)
+    constexpr int USEDP = ((C - 1) * CS + D + 7) / 8 * 8;
     constexpr int DJB = (D + 31) / 32;
-    constexpr uint32_t kSlab = 4u * D * 128u;        // one codebook's A slab: 4 row blocks x [D][128 B]
+    constexpr uint32_t kBlk = (uint32_t)USEDP * 128u;   // one 32-row block of the slab
+    constexpr uint32_t kStage = 4u * kBlk;
     constexpr uint32_t kEcb = (uint32_t)DJB * NK * 128u;
+    static_assert(C * NK <= 256, "accumulator columns");
     uint8_t* a_s = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* e_s = a_s + (size_t)C * kSlab;
+    uint8_t* e_s = a_s + (size_t)NSTAGE * kStage;
     float* ee_s = reinterpret_cast<float*>(e_s + (size_t)C * kEcb);  // [C][NK]
     float* emax_s = ee_s + C * NK;                                   // [C] (+pad)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(emax_s + ((C + 3) & ~3));
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(emax_s + ((C + 3) & ~3));  // full[NSTAGE], mma
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSTAGE + 1);
     const uint32_t a_base = smem_u32(a_s), e_base = smem_u32(e_s);
-    const uint32_t bar_a = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1]);
+    const uint32_t bar_full0 = smem_u32(&bars[0]), bar_m = smem_u32(&bars[NSTAGE]);
 
     if (tid == 0) {
-        mbar_init(bar_a, 1);
+        for (int i = 0; i < NSTAGE; ++i) mbar_init(bar_full0 + 8 * i, 1);
         mbar_init(bar_m, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+    __syncthreads();  // barriers initialised before the first TMA may signal them
+
+    const int niter = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto issue = [&](int it) {  // thread 0 only: TMA-load the tile of iteration `it` into its ring slot
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int seg = tile / p.tiles_per_seg;
+        const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
+        const int st = it % NSTAGE;
+        int nblk = 0;
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) nblk += (row0 + 32 * mb < p.N) ? 1 : 0;
+        mbar_expect_tx(bar_full0 + 8 * st, (uint32_t)nblk * kBlk);
+        for (int mb = 0; mb < nblk; ++mb) {
+            const long long nb = row0 + 32 * mb;
+            const long long bb = nb / HWT;
+            tma_load_3d(a_base + st * kStage + mb * kBlk, &maps.m[seg], bar_full0 + 8 * st, (int)(nb - bb * HWT), 0, (int)bb);
+        }
+    };
+    if (tid == 0)
+        for (int it = 0; it < NSTAGE - 1 && it < niter; ++it) issue(it);
+
     // ---- codebooks -> K-major SWIZZLE_128B tiles (once per persistent CTA) + |e|^2 ----------------------------
     for (int i = tid; i < C * NK * DJB * 32; i += kFT) {
         const int j = i % (DJB * 32), ck = i / (DJB * 32), k = ck % NK, c = ck / NK;
@@ -97,51 +128,46 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
     const uint32_t tmem_base = *tmem_slot;
     __syncthreads();
 
-    // lane-dependent pieces of the swizzled addresses
-    uint32_t zsw[4];  // byte offset of (this lane's row, channel j) inside a row block, minus j*128, for j & 3 = x
+    // lane-dependent part of the swizzled z address, indexed by (channel & 3) relative to this warpgroup's first slice
+    uint32_t zsw[4];
 #pragma unroll
-    for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ x) & 3) << 5) + ((lane & 7) << 2);
+    for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ (x + wg * CS)) & 3) << 5) + ((lane & 7) << 2);
 
-    uint32_t phase_a = 0, phase_m = 0;
+    uint32_t phase_m = 0;
     float lsum[CPW];
 #pragma unroll
     for (int ci = 0; ci < CPW; ++ci) lsum[ci] = 0.0f;
 
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    for (int it = 0; it < niter; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
         const int seg = tile / p.tiles_per_seg;
         const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
         const long long n = row0 + quarter * 32 + lane;
         const bool valid = n < p.N;  // warp-uniform (N is a multiple of 32)
         const long long b = n / HWT;
         const int hw = (int)(n - b * HWT);
+        const int st = it % NSTAGE;
         if (tid == 0) {
-            int nblk = 0;
-#pragma unroll
-            for (int mb = 0; mb < 4; ++mb) nblk += (row0 + 32 * mb < p.N) ? 1 : 0;
-            mbar_expect_tx(bar_a, (uint32_t)(C * nblk) * D * 128u);
-            for (int c = 0; c < C; ++c)
-                for (int mb = 0; mb < nblk; ++mb) {
-                    const long long nb = row0 + 32 * mb;
-                    const long long bb = nb / HWT;
-                    tma_load_3d(a_base + c * kSlab + mb * D * 128u, &maps.m[seg], bar_a, (int)(nb - bb * HWT), c * p.cs,
-                                (int)bb);
-                }
+            if (NSTAGE == 1) issue(it);
+            else if (it + NSTAGE - 1 < niter) issue(it + NSTAGE - 1);  // slot consumed in iteration it-1
         }
-        mbar_wait(bar_a, phase_a);
-        phase_a ^= 1;
+        mbar_wait_fast(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
         tc_fence_after();
+        const uint32_t stage_u32 = a_base + st * kStage;
         if (tid == 0) {
             const uint32_t idesc = instr_desc_tf32(NK);
+#pragma unroll
             for (int c = 0; c < C; ++c) {
 #pragma unroll
                 for (int s = 0; s < D / 8; ++s) {
-                    const uint64_t ad = smem_desc(a_base + c * kSlab + s * 1024u, D * 128u, 512u, 1u);
+                    const uint64_t ad = smem_desc(stage_u32 + (uint32_t)(c * CS + 8 * s) * 128u, kBlk, 512u, 1u);
                     const uint64_t bd = smem_desc(e_base + c * kEcb + (s >> 2) * NK * 128u + (s & 3) * 32u, 16u, 1024u, 2u);
                     umma_tf32(tmem_base + c * NK, ad, bd, idesc, s > 0 ? 1u : 0u);
                 }
             }
             umma_commit(bar_m);
         }
+        const uint8_t* zblk = a_s + st * kStage + quarter * kBlk + wg * CS * 128;  // this warpgroup's first slice, this row block
         // |z|^2 of this thread's row for its codebooks while the tensor core works (exact sequential chains)
         float zz[CPW];
         if (valid) {
@@ -151,15 +177,15 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
             for (int j = 0; j < D; ++j) {
 #pragma unroll
                 for (int ci = 0; ci < CPW; ++ci) {
-                    const int c = wg + 2 * ci;
-                    if (c < C) {
-                        const float v = *reinterpret_cast<const float*>(a_s + c * kSlab + quarter * (D * 128u) + j * 128 + zsw[j & 3]);
+                    if (wg + 2 * ci < C) {
+                        constexpr int dummy = 0; (void)dummy;
+                        const float v = *reinterpret_cast<const float*>(zblk + (2 * ci * CS + j) * 128 + zsw[(2 * ci * CS + j) & 3]);
                         zz[ci] = fmaf(v, v, zz[ci]);
                     }
                 }
             }
         }
-        mbar_wait(bar_m, phase_m);
+        mbar_wait_fast(bar_m, phase_m);
         phase_m ^= 1;
         tc_fence_after();
 
@@ -170,7 +196,7 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                 if (c >= C) continue;
                 const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + c * NK;
                 const float* ee = ee_s + c * NK;
-                const uint8_t* zrow = a_s + c * kSlab + quarter * (D * 128u);
+                const uint8_t* zc = zblk + 2 * ci * CS * 128;  // channel j of codebook c sits at zc + j*128 + zsw[(2ciCS+j)&3]
                 const uint8_t* ecb = e_s + (size_t)c * kEcb;
                 constexpr int NCH = NK / 64;
                 float a[64];
@@ -190,10 +216,11 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                     }
                 }
                 const float mn = fminf(fminf(m0, m1), fminf(m2, m3));
-                // rigorous bound on |tf32 distance - exact-chain distance|
+                // rigorous bound on |tf32 distance - exact-chain distance|: both operands lose at most
+                // 2^-10 relative (truncation to 10 mantissa bits) -> |dot error| <= (2^-9 + slack) |z||e|
                 const float emax = emax_s[c];
                 const float zzc = zz[ci];
-                const float thr = 2.0f * (0.00390625f * sqrtf(zzc) * 1.0001f * emax + 9.5367431640625e-7f * (zzc + emax * emax));
+                const float thr = 2.0f * (2.0f * 2.05e-3f * sqrtf(zzc) * 1.0001f * emax + 9.5367431640625e-7f * (zzc + emax * emax));
                 const float lim = mn + thr;
                 // ---- pass 2: survivors as a bitmask ------------------------------------------------------------------------
                 unsigned mask[NCH * 2];
@@ -214,8 +241,8 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                     unsigned lo = 0u, hi = 0u;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        if (a[i] <= lim) lo |= 1u << i;
-                        if (a[32 + i] <= lim) hi |= 1u << i;
+                        or_if_le(lo, a[i], lim, 1u << i);
+                        or_if_le(hi, a[32 + i], lim, 1u << i);
                     }
                     mask[2 * chn] = lo;
                     mask[2 * chn + 1] = hi;
@@ -238,7 +265,7 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                             float dot = 0.0f;
 #pragma unroll
                             for (int j = 0; j < D; ++j)
-                                dot = fmaf(*reinterpret_cast<const float*>(zrow + j * 128 + zsw[j & 3]),
+                                dot = fmaf(*reinterpret_cast<const float*>(zc + j * 128 + zsw[(2 * ci * CS + j) & 3]),
                                            *reinterpret_cast<const float*>(erow + (j >> 5) * NK * 128 +
                                                                            (((((j & 31) >> 2) ^ (k & 7)) & 7) << 4) + ((j & 3) << 2)), dot);
                             const float dist = dist_f32(zzc, ee[k], dot);
@@ -258,10 +285,10 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                                 for (int j = 0; j < D; j += 4) {
                                     const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 +
                                                                                        ((((j & 31) >> 2) << 4) ^ kx));
-                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + j * 128 + zsw[j & 3]), e4.x, dot);
-                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + (j + 1) * 128 + zsw[(j + 1) & 3]), e4.y, dot);
-                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + (j + 2) * 128 + zsw[(j + 2) & 3]), e4.z, dot);
-                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + (j + 3) * 128 + zsw[(j + 3) & 3]), e4.w, dot);
+                                    dot = fmaf(*reinterpret_cast<const float*>(zc + j * 128 + zsw[(2 * ci * CS + j) & 3]), e4.x, dot);
+                                    dot = fmaf(*reinterpret_cast<const float*>(zc + (j + 1) * 128 + zsw[(2 * ci * CS + j + 1) & 3]), e4.y, dot);
+                                    dot = fmaf(*reinterpret_cast<const float*>(zc + (j + 2) * 128 + zsw[(2 * ci * CS + j + 2) & 3]), e4.z, dot);
+                                    dot = fmaf(*reinterpret_cast<const float*>(zc + (j + 3) * 128 + zsw[(2 * ci * CS + j + 3) & 3]), e4.w, dot);
                                 }
                                 const float dist = dist_f32(zzc, ee[k], dot);
                                 if (dist < bv) { bv = dist; bi = k; }  // ascending k: strict '<' keeps the first minimum
@@ -279,10 +306,10 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
 #pragma unroll
                     for (int j = 0; j < D; j += 4) {
                         const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 + ((((j & 31) >> 2) << 4) ^ kx));
-                        const float z0 = *reinterpret_cast<const float*>(zrow + j * 128 + zsw[j & 3]);
-                        const float z1 = *reinterpret_cast<const float*>(zrow + (j + 1) * 128 + zsw[(j + 1) & 3]);
-                        const float z2 = *reinterpret_cast<const float*>(zrow + (j + 2) * 128 + zsw[(j + 2) & 3]);
-                        const float z3 = *reinterpret_cast<const float*>(zrow + (j + 3) * 128 + zsw[(j + 3) & 3]);
+                        const float z0 = *reinterpret_cast<const float*>(zc + j * 128 + zsw[(2 * ci * CS + j) & 3]);
+                        const float z1 = *reinterpret_cast<const float*>(zc + (j + 1) * 128 + zsw[(2 * ci * CS + j + 1) & 3]);
+                        const float z2 = *reinterpret_cast<const float*>(zc + (j + 2) * 128 + zsw[(2 * ci * CS + j + 2) & 3]);
+                        const float z3 = *reinterpret_cast<const float*>(zc + (j + 3) * 128 + zsw[(2 * ci * CS + j + 3) & 3]);
                         const float d0 = __fsub_rn(e4.x, z0), d1 = __fsub_rn(e4.y, z1);
                         const float d2 = __fsub_rn(e4.z, z2), d3 = __fsub_rn(e4.w, z3);
                         out[(size_t)j * HWT] = __fadd_rn(z0, d0);  // z + (q - z), models/vq_vae.py:53
@@ -297,7 +324,7 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
             }
         }
         tc_fence_before();
-        __syncthreads();  // TMEM columns and the A slabs are free again
+        __syncthreads();  // TMEM columns and this ring slot are free again
     }
     // ---- loss: warp sums -> fp64 atomics -> last CTA finalises -----------------------------------------------------
     if (p.fused) {
@@ -335,19 +362,20 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-template <int D, int NK, int HWT, int CPW>
+template <int D, int NK, int HWT, int C, int CS, int NSTAGE>
 int launch_fast(const QuantParams& p0, cudaStream_t s) {
     FastParams P;
     P.q = p0;
     P.q.tiles_per_seg = (int)((p0.N + kTM - 1) / kTM);
     P.ntiles = P.q.tiles_per_seg * p0.n_seg;
-    Maps maps;
-    if (make_maps(p0, maps) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
+    constexpr int USEDP = ((C - 1) * CS + D + 7) / 8 * 8;
     constexpr int DJB = (D + 31) / 32;
-    const size_t smem = (size_t)p0.C * 4 * D * 128 + (size_t)p0.C * DJB * NK * 128 +
-                        sizeof(float) * ((size_t)p0.C * NK + ((p0.C + 3) & ~3)) + 2 * 8 + 16 + 1024;
-    if (smem > 113 * 1024) return CTVQ_E_UNSUPPORTED;
-    auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, CPW>;
+    Maps maps;
+    if (make_maps(p0, maps, USEDP) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
+    constexpr size_t smem = (size_t)NSTAGE * 4 * USEDP * 128 + (size_t)C * DJB * NK * 128 +
+                            sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (NSTAGE + 1) * 8 + 16 + 1024;
+    static_assert(smem <= 113 * 1024, "two CTAs per SM");
+    auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, C, CS, NSTAGE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int grid = 148 * 2;
@@ -360,12 +388,14 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
 
 // Shapes with a specialised kernel; anything else falls through to the generic tcgen05 kernel / SIMT.
 int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
-    if (p.HW % 32 != 0 || p.K > 64 || p.C > 4) return CTVQ_E_UNSUPPORTED;
+    if (p.HW % 32 != 0 || p.K > 64) return CTVQ_E_UNSUPPORTED;
     for (int sg = 0; sg < p.n_seg; ++sg)
         if (reinterpret_cast<uintptr_t>(p.z[sg]) & 15) return CTVQ_E_UNSUPPORTED;
     if (!encode_fn()) return CTVQ_E_UNSUPPORTED;
-    if (p.d == 32 && p.HW == 64 && p.C <= 4) return p.C <= 2 ? launch_fast<32, 64, 64, 1>(p, s) : launch_fast<32, 64, 64, 2>(p, s);
-    if (p.d == 128 && p.HW == 64 && p.C == 1) return launch_fast<128, 64, 64, 1>(p, s);
+    // configs/mcq_vae.yaml: C=4 codebooks x d=32 on overlapping slices of [B,128,8,8]
+    if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) return launch_fast<32, 64, 64, 4, 1, 3>(p, s);
+    // configs/ct_mcq_vae.yaml: C=1, d=128
+    if (p.d == 128 && p.HW == 64 && p.C == 1) return launch_fast<128, 64, 64, 1, 1, 1>(p, s);
     return CTVQ_E_UNSUPPORTED;
 }
 

@@ -31,6 +31,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a barrier that never completes traps instead of hanging the GPU.
+// Hot-path wait: try_wait with a suspend-time hint sleeps in hardware until the phase completes (or ~1 ms
+// passes), so the loop body runs once or twice; 2048 expiries (~2 s) trap instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+    for (int it = 0; it < 2048; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -123,8 +137,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_fn();
-// 3-D tensor maps over the NCHW latents [B][Dtot][HW], box = 32 rows x d channels, SWIZZLE_128B_ATOM_32B
-int make_maps(const QuantParams& p, Maps& maps);
+// 3-D tensor maps over the NCHW latents [B][Dtot][HW], box = 32 rows x box_channels (0: d), SWIZZLE_128B_ATOM_32B
+int make_maps(const QuantParams& p, Maps& maps, int box_channels);
 
 }  // namespace tc
 }  // namespace ctvq
