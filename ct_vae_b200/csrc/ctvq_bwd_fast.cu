@@ -44,32 +44,49 @@ __global__ void __launch_bounds__(kBT, 2) vq_bwd_fast_kernel(const BwdParams p, 
     const float coef_e = (float)(2.0 / nd) * gl;
     const float coef_z = (float)(2.0 * (double)p.beta / nd) * gl;
 
+    // ---- register prefetch of a tile's staging data (indices + touched z channels), one tile ahead ---------------
+    constexpr int NZ = (USED + 1) / 2;        // z channels per thread (thread = row m, channel parity tid/128)
+    constexpr int NI = (C + 1) / 2;
+    float zreg[NZ];
+    int kreg[NI];
+    const int sm_m = tid & (kTM - 1), sm_par = tid / kTM;
+    auto prefetch = [&](int tile) {
+        const long long row0 = (long long)tile * kTM;
+        const long long n = row0 + sm_m;
+        const bool valid = n < p.N;
+        const long long b = valid ? n / HWT : 0;
+        const int hw = valid ? (int)(n - b * HWT) : 0;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int c = sm_par + 2 * i;
+            int k = 0;
+            if (valid && c < C) {
+                const long long kk = __ldg(p.idx + ((size_t)b * C + c) * HWT + hw);
+                if (kk < 0 || kk >= K) { atomicOr(p.err, 1u); k = kk < 0 ? 0 : K - 1; } else k = (int)kk;
+            }
+            kreg[i] = k;
+        }
+        const float* src = p.z + (size_t)b * DTOT * HWT + hw;
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) {
+            const int ch = sm_par + 2 * i;
+            zreg[i] = (valid && ch < USED) ? __ldg(src + (size_t)ch * HWT) : 0.0f;
+        }
+    };
+    if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x);
+
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long row0 = (long long)tile * kTM;
         const int mcount = (int)min((long long)kTM, p.N - row0);
-        __syncthreads();
-        // ---- stage indices and the z channels the slices touch (coalesced along H*W) ---------------------------------
-        {
-            const int m = tid & (kTM - 1);
-            const bool valid = m < mcount;
-            const long long n = row0 + m;
-            const long long b = valid ? n / HWT : 0;
-            const int hw = valid ? (int)(n - b * HWT) : 0;
+        __syncthreads();  // previous tile fully consumed
 #pragma unroll
-            for (int c = tid / kTM; c < C; c += kBT / kTM) {
-                int k = 0;
-                if (valid) {
-                    const long long kk = __ldg(p.idx + ((size_t)b * C + c) * HWT + hw);
-                    if (kk < 0 || kk >= K) { atomicOr(p.err, 1u); k = kk < 0 ? 0 : K - 1; } else k = (int)kk;
-                }
-                idx_s[c * kTM + m] = k;
-            }
-            const float* src = p.z + (size_t)b * DTOT * HWT + hw;
-#pragma unroll 6
-            for (int ch = tid / kTM; ch < USED; ch += kBT / kTM)
-                zs[ch * ZS + m] = valid ? __ldg(src + (size_t)ch * HWT) : 0.0f;
-        }
+        for (int i = 0; i < NI; ++i)
+            if (sm_par + 2 * i < C) idx_s[(sm_par + 2 * i) * kTM + sm_m] = kreg[i];
+#pragma unroll
+        for (int i = 0; i < NZ; ++i)
+            if (sm_par + 2 * i < USED) zs[(sm_par + 2 * i) * ZS + sm_m] = zreg[i];
         __syncthreads();
+        if (tile + (int)gridDim.x < ntiles) prefetch(tile + gridDim.x);  // latency hidden behind this tile's work
         if (warp >= 4) {
             // ---- grad_z: warp handles channels ch = (warp-4) + 4*i; lane handles rows 4*lane .. 4*lane+3 -------------
             const int m = lane * 4;
@@ -86,31 +103,39 @@ __global__ void __launch_bounds__(kBT, 2) vq_bwd_fast_kernel(const BwdParams p, 
                     eb[c][0] = (c * K + kk.x) * ESD; eb[c][1] = (c * K + kk.y) * ESD;
                     eb[c][2] = (c * K + kk.z) * ESD; eb[c][3] = (c * K + kk.w) * ESD;
                 }
-                for (int ch = warp - 4; ch < DTOT; ch += 4) {
+                auto load_go = [&](int ch, float4 (&go)[C]) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int j = ch - c * CS;
+                        go[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ch < USED && j >= 0 && j < D && go_row)
+                            go[c] = __ldg(reinterpret_cast<const float4*>(go_row + (size_t)(c * D + j) * HWT));
+                    }
+                };
+                // channels that no slice reads: zeros, no loads (issued first so the stores drain under the loads)
+                for (int ch = USED + ((warp - 4) - USED % 4 + 4) % 4; ch < DTOT; ch += 4)
+                    *reinterpret_cast<float4*>(gz_row + (size_t)ch * HWT) = make_float4(0.f, 0.f, 0.f, 0.f);
+                // active channels, software-pipelined: the next channel's g_out loads fly while this one is computed
+                float4 go_cur[C], go_nxt[C];
+                int ch = warp - 4;
+                load_go(ch, go_cur);
+                for (; ch < USED; ch += 4) {
+                    load_go(ch + 4, go_nxt);
+                    const float z0 = zs[ch * ZS + m], z1 = zs[ch * ZS + m + 1], z2 = zs[ch * ZS + m + 2], z3 = zs[ch * ZS + m + 3];
                     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ch < USED) {
-                        const float z0 = zs[ch * ZS + m], z1 = zs[ch * ZS + m + 1], z2 = zs[ch * ZS + m + 2],
-                                    z3 = zs[ch * ZS + m + 3];
-                        float4 go[C];
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const int j = ch - c * CS;
-                            go[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (j >= 0 && j < D && go_row)
-                                go[c] = __ldg(reinterpret_cast<const float4*>(go_row + (size_t)(c * D + j) * HWT));
-                        }
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const int j = ch - c * CS;
-                            if (j >= 0 && j < D) {
-                                const float d0 = __fsub_rn(es[eb[c][0] + j], z0), d1 = __fsub_rn(es[eb[c][1] + j], z1);
-                                const float d2 = __fsub_rn(es[eb[c][2] + j], z2), d3 = __fsub_rn(es[eb[c][3] + j], z3);
-                                g.x += go[c].x - coef_z * d0; g.y += go[c].y - coef_z * d1;
-                                g.z += go[c].z - coef_z * d2; g.w += go[c].w - coef_z * d3;
-                            }
+                    for (int c = 0; c < C; ++c) {
+                        const int j = ch - c * CS;
+                        if (j >= 0 && j < D) {
+                            const float d0 = __fsub_rn(es[eb[c][0] + j], z0), d1 = __fsub_rn(es[eb[c][1] + j], z1);
+                            const float d2 = __fsub_rn(es[eb[c][2] + j], z2), d3 = __fsub_rn(es[eb[c][3] + j], z3);
+                            g.x += go_cur[c].x - coef_z * d0; g.y += go_cur[c].y - coef_z * d1;
+                            g.z += go_cur[c].z - coef_z * d2; g.w += go_cur[c].w - coef_z * d3;
                         }
                     }
                     *reinterpret_cast<float4*>(gz_row + (size_t)ch * HWT) = g;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) go_cur[c] = go_nxt[c];
                 }
             }
         } else if (warp < ITEMS) {
