@@ -212,6 +212,8 @@ typedef int (*fn_comm_init_rank)(void**, int, NcclUniqueId, int);
 typedef int (*fn_comm_destroy)(void*);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*fn_get_error_string)(int);
+typedef int (*fn_redop_create_premulsum)(int*, void*, int, int, void*);
+typedef int (*fn_redop_destroy)(int, void*);
 struct NcclApi {
     void* handle = nullptr;
     fn_get_unique_id get_unique_id = nullptr;
@@ -219,6 +221,8 @@ struct NcclApi {
     fn_comm_destroy comm_destroy = nullptr;
     fn_all_reduce all_reduce = nullptr;
     fn_get_error_string error_string = nullptr;
+    fn_redop_create_premulsum premulsum = nullptr;
+    fn_redop_destroy redop_destroy = nullptr;
 } g_nccl;
 constexpr int kNcclFloat32 = 7;  // ncclFloat32
 constexpr int kNcclSum = 0;      // ncclSum
@@ -237,6 +241,8 @@ int ctvq_nccl_load(const char* path) {
     g_nccl.comm_destroy = (fn_comm_destroy)dlsym(h, "ncclCommDestroy");
     g_nccl.all_reduce = (fn_all_reduce)dlsym(h, "ncclAllReduce");
     g_nccl.error_string = (fn_get_error_string)dlsym(h, "ncclGetErrorString");
+    g_nccl.premulsum = (fn_redop_create_premulsum)dlsym(h, "ncclRedOpCreatePreMulSum");
+    g_nccl.redop_destroy = (fn_redop_destroy)dlsym(h, "ncclRedOpDestroy");
     if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.comm_destroy || !g_nccl.all_reduce) return CTVQ_E_NCCL;
     g_nccl.handle = h;
     return CTVQ_OK;
@@ -275,6 +281,20 @@ int ctvq_allreduce_codebook_grad(void* comm, float* gE, size_t count, float scal
     DeviceGuard g(device);
     if (g.err != cudaSuccess) return (int)g.err;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // scale folded into the reduction (sum of scale*x): ONE NCCL kernel, no separate scaling pass
+    if (scale != 1.0f && g_nccl.premulsum && g_nccl.redop_destroy) {
+        int op = 0;
+        float sc = scale;
+        if (g_nccl.premulsum(&op, &sc, kNcclFloat32, /*ncclScalarHostImmediate*/ 1, comm) == 0) {
+            const int rc = g_nccl.all_reduce(gE, gE, count, kNcclFloat32, op, comm, s);
+            g_nccl.redop_destroy(op, comm);
+            if (rc != 0) {
+                fprintf(stderr, "ctvq: ncclAllReduce failed: %s\n", g_nccl.error_string ? g_nccl.error_string(rc) : "?");
+                return CTVQ_E_NCCL;
+            }
+            return CTVQ_OK;
+        }
+    }
     const int rc = g_nccl.all_reduce(gE, gE, count, kNcclFloat32, kNcclSum, comm, s);
     if (rc != 0) {
         fprintf(stderr, "ctvq: ncclAllReduce failed: %s\n", g_nccl.error_string ? g_nccl.error_string(rc) : "?");
