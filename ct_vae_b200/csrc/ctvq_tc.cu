@@ -118,6 +118,10 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
         mbar_wait(bar_a, phase_a);
         phase_a ^= 1;
 
+        // exact running best across the column chunks of one codebook (only used when a codebook spans > 256 codes)
+        float run_mn = CUDART_INF_F, run_bv = CUDART_INF_F;
+        int run_bi = 0x7fffffff;
+        bool run_bad = false;
         for (int u0 = 0; u0 < P.units;) {
             // ---- pack units (codebook, column chunk) into <= 256 TMEM columns --------------------------------------
             int u1 = u0, cols = 0;
@@ -177,7 +181,9 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
                 // rigorous bound on |tf32 distance - exact-chain distance|: operands truncated to 11 bits
                 const float emax = emax_s[c];
                 const float thr = 2.0f * (0.00390625f * sqrtf(zz) * 1.0001f * emax + 9.5367431640625e-7f * (zz + emax * emax));
-                const float lim = mn + thr;
+                if (ch == 0) { run_mn = CUDART_INF_F; run_bv = CUDART_INF_F; run_bi = 0x7fffffff; run_bad = false; }
+                run_mn = fminf(run_mn, mn);
+                const float lim = run_mn + thr;  // running minimum: a superset of the final survivor set
                 // pass 2: survivors
                 unsigned mask[kMaxBlk];
                 int cnt = 0;
@@ -198,44 +204,51 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
                 if (valid) {
                     float bv;
                     int bi;
-                    const bool finite = (zz < CUDART_INF_F) && (mn > -CUDART_INF_F) && (mn < CUDART_INF_F) && cnt >= 1;
-                    if (!finite) {
-                        // non-finite row: exact scan of every code of this chunk with torch.argmin's NaN rule
-                        bv = CUDART_INF_F; bi = 0x7fffffff;
-                        for (int k = 0; k < K; ++k) {
-                            float dot = 0.0f;
-                            for (int j = 0; j < d; ++j)
-                                dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j)),
-                                           *reinterpret_cast<const float*>(ecb + e_off(k, j, Kpad)), dot);
-                            const float dist = dist_f32(zz, ee_s[c * Kpad + k], dot);
-                            if (!(dist >= bv) && (bv == bv)) { bv = dist; bi = k; }
-                        }
-                    } else if (cnt == 1) {
+                    const bool multi = P.chunks > 1;
+                    const bool last = ch == P.chunks - 1;
+                    const bool finite = (zz < CUDART_INF_F) && (mn > -CUDART_INF_F) && (mn < CUDART_INF_F) && (multi || cnt >= 1);
+                    if (!finite) run_bad = true;
+                    if (!multi && finite && cnt == 1) {
                         bv = 0.0f; bi = 0;
 #pragma unroll
                         for (int blk = 0; blk < kMaxBlk; ++blk) if (mask[blk]) bi = blk * 32 + __ffs(mask[blk]) - 1;
                     } else {
-                        bv = CUDART_INF_F; bi = 0x7fffffff;
+                        if (finite) {
 #pragma unroll
-                        for (int blk = 0; blk < kMaxBlk; ++blk) {
-                            unsigned mk = mask[blk];
-                            while (mk) {
-                                const int i = __ffs(mk) - 1;
-                                mk &= mk - 1;
-                                const int k = ch * 256 + blk * 32 + i;
-                                float dot = 0.0f;
-                                for (int j = 0; j < d; j += 4) {
-                                    const float4 e4 = *reinterpret_cast<const float4*>(ecb + e_off(k, j, Kpad));
-                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j)), e4.x, dot);
-                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j + 1)), e4.y, dot);
-                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j + 2)), e4.z, dot);
-                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j + 3)), e4.w, dot);
+                            for (int blk = 0; blk < kMaxBlk; ++blk) {
+                                unsigned mk = mask[blk];
+                                while (mk) {
+                                    const int i = __ffs(mk) - 1;
+                                    mk &= mk - 1;
+                                    const int k = ch * 256 + blk * 32 + i;
+                                    float dot = 0.0f;
+                                    for (int j = 0; j < d; j += 4) {
+                                        const float4 e4 = *reinterpret_cast<const float4*>(ecb + e_off(k, j, Kpad));
+                                        dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j)), e4.x, dot);
+                                        dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j + 1)), e4.y, dot);
+                                        dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j + 2)), e4.z, dot);
+                                        dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j + 3)), e4.w, dot);
+                                    }
+                                    const float dist = dist_f32(zz, ee_s[c * Kpad + k], dot);
+                                    if (dist < run_bv) { run_bv = dist; run_bi = k; }  // ascending k: strict '<' keeps the first minimum
                                 }
-                                const float dist = dist_f32(zz, ee_s[c * Kpad + k], dot);
-                                if (dist < bv) { bv = dist; bi = k; }  // ascending k: strict '<' keeps the first minimum
                             }
                         }
+                        if (last && (run_bad || run_bi == 0x7fffffff)) {
+                            // non-finite row: exact scan of every code with torch.argmin's NaN rule
+                            run_bv = CUDART_INF_F; run_bi = 0x7fffffff;
+                            for (int k = 0; k < K; ++k) {
+                                float dot = 0.0f;
+                                for (int j = 0; j < d; ++j)
+                                    dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j)),
+                                               *reinterpret_cast<const float*>(ecb + e_off(k, j, Kpad)), dot);
+                                const float dist = dist_f32(zz, ee_s[c * Kpad + k], dot);
+                                if (!(dist >= run_bv) && (run_bv == run_bv)) { run_bv = dist; run_bi = k; }
+                            }
+                        }
+                        bv = run_bv; bi = run_bi;
                     }
+                    if (last) {
                     (void)bv;
                     p.idx[seg][((size_t)b * C + c) * HW + hw] = (long long)bi;
                     // ---- fused gather + straight-through + loss --------------------------------------------------------
@@ -255,6 +268,7 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
                         }
                         lsum_s[c * kThreads + tid] += ls;
                     }
+                    }  // last chunk of this codebook
                 }
                 col += w;
             }
@@ -310,9 +324,8 @@ Plan make_plan(const QuantParams& p) {
     Plan pl;
     if (p.HW % 32 != 0 || p.d % 8 != 0 || p.d > 256 || p.d < 8) return pl;
     pl.Kpad = (p.K + 15) / 16 * 16;
-    if (pl.Kpad > 256) return pl;        // one column chunk per codebook (this version)
-    pl.chunks = 1;
-    pl.units = p.C;
+    pl.chunks = (pl.Kpad + 255) / 256;   // codebooks wider than 256 codes take several 256-column rounds
+    pl.units = p.C * pl.chunks;
     pl.djb = (p.d + 31) / 32;
     pl.a_bytes = (size_t)p.C * 4 * p.d * 128;
     pl.e_bytes = (size_t)p.C * pl.djb * pl.Kpad * 128;

@@ -67,14 +67,14 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
     uint8_t* e_s = a_s + (size_t)NSTAGE * kStage;
     float* ee_s = reinterpret_cast<float*>(e_s + (size_t)C * kEcb);  // [C][NK]
     float* emax_s = ee_s + C * NK;                                   // [C] (+pad)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(emax_s + ((C + 3) & ~3));  // full[NSTAGE], mma
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSTAGE + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(emax_s + ((C + 3) & ~3));  // full[NSTAGE], mma[C]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSTAGE + C);
     const uint32_t a_base = smem_u32(a_s), e_base = smem_u32(e_s);
     const uint32_t bar_full0 = smem_u32(&bars[0]), bar_m = smem_u32(&bars[NSTAGE]);
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) mbar_init(bar_full0 + 8 * i, 1);
-        mbar_init(bar_m, 1);
+        for (int c = 0; c < C; ++c) mbar_init(bar_m + 8 * c, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                     const uint64_t bd = smem_desc(e_base + c * kEcb + (s >> 2) * NK * 128u + (s & 3) * 32u, 16u, 1024u, 2u);
                     umma_tf32(tmem_base + c * NK, ad, bd, idesc, s > 0 ? 1u : 0u);
                 }
+                umma_commit(bar_m + 8 * c);  // per-codebook completion: its epilogue starts while later codebooks multiply
             }
-            umma_commit(bar_m);
         }
         const uint8_t* zblk = a_s + st * kStage + quarter * kBlk + wg * CS * 128;  // this warpgroup's first slice, this row block
         // |z|^2 of this thread's row for its codebooks while the tensor core works (exact sequential chains)
@@ -178,22 +178,19 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
 #pragma unroll
                 for (int ci = 0; ci < CPW; ++ci) {
                     if (wg + 2 * ci < C) {
-                        constexpr int dummy = 0; (void)dummy;
                         const float v = *reinterpret_cast<const float*>(zblk + (2 * ci * CS + j) * 128 + zsw[(2 * ci * CS + j) & 3]);
                         zz[ci] = fmaf(v, v, zz[ci]);
                     }
                 }
             }
         }
-        mbar_wait_fast(bar_m, phase_m);
-        phase_m ^= 1;
-        tc_fence_after();
-
-        if (valid) {
 #pragma unroll
-            for (int ci = 0; ci < CPW; ++ci) {
-                const int c = wg + 2 * ci;
-                if (c >= C) continue;
+        for (int ci = 0; ci < CPW; ++ci) {
+            const int c = wg + 2 * ci;
+            if (c >= C) continue;
+            mbar_wait_fast(bar_m + 8 * c, phase_m);
+            tc_fence_after();
+            if (valid) {
                 const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + c * NK;
                 const float* ee = ee_s + c * NK;
                 const uint8_t* zc = zblk + 2 * ci * CS * 128;  // channel j of codebook c sits at zc + j*128 + zsw[(2ciCS+j)&3]
@@ -323,6 +320,7 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                 }
             }
         }
+        phase_m ^= 1;
         tc_fence_before();
         __syncthreads();  // TMEM columns and this ring slot are free again
     }
@@ -373,7 +371,7 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
     Maps maps;
     if (make_maps(p0, maps, USEDP) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
     constexpr size_t smem = (size_t)NSTAGE * 4 * USEDP * 128 + (size_t)C * DJB * NK * 128 +
-                            sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (NSTAGE + 1) * 8 + 16 + 1024;
+                            sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (NSTAGE + C) * 8 + 16 + 1024;
     static_assert(smem <= 113 * 1024, "two CTAs per SM");
     auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, C, CS, NSTAGE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
