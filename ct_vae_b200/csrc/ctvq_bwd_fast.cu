@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kBT, 2) vq_bwd_fast_kernel(const BwdParams p, 
     constexpr int NZ = (USED + 1) / 2;        // z channels per thread (thread = row m, channel parity tid/128)
     constexpr int NI = (C + 1) / 2;
     float zreg[NZ];
-    int kreg[NI];
+    long long kreg[NI];  // raw int64 indices: validated when they are stored to shared memory, not when loaded
     const int sm_m = tid & (kTM - 1), sm_par = tid / kTM;
     auto prefetch = [&](int tile) {
         const long long row0 = (long long)tile * kTM;
@@ -59,12 +59,7 @@ __global__ void __launch_bounds__(kBT, 2) vq_bwd_fast_kernel(const BwdParams p, 
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const int c = sm_par + 2 * i;
-            int k = 0;
-            if (valid && c < C) {
-                const long long kk = __ldg(p.idx + ((size_t)b * C + c) * HWT + hw);
-                if (kk < 0 || kk >= K) { atomicOr(p.err, 1u); k = kk < 0 ? 0 : K - 1; } else k = (int)kk;
-            }
-            kreg[i] = k;
+            kreg[i] = (valid && c < C) ? __ldg(p.idx + ((size_t)b * C + c) * HWT + hw) : 0;
         }
         const float* src = p.z + (size_t)b * DTOT * HWT + hw;
 #pragma unroll
@@ -81,12 +76,27 @@ __global__ void __launch_bounds__(kBT, 2) vq_bwd_fast_kernel(const BwdParams p, 
         __syncthreads();  // previous tile fully consumed
 #pragma unroll
         for (int i = 0; i < NI; ++i)
-            if (sm_par + 2 * i < C) idx_s[(sm_par + 2 * i) * kTM + sm_m] = kreg[i];
+            if (sm_par + 2 * i < C) {
+                long long kk = kreg[i];
+                if (kk < 0 || kk >= K) { atomicOr(p.err, 1u); kk = kk < 0 ? 0 : K - 1; }
+                idx_s[(sm_par + 2 * i) * kTM + sm_m] = (int)kk;
+            }
 #pragma unroll
         for (int i = 0; i < NZ; ++i)
             if (sm_par + 2 * i < USED) zs[(sm_par + 2 * i) * ZS + sm_m] = zreg[i];
         __syncthreads();
-        if (tile + (int)gridDim.x < ntiles) prefetch(tile + gridDim.x);  // latency hidden behind this tile's work
+        if (tile + (int)gridDim.x < ntiles) {
+            prefetch(tile + gridDim.x);  // latency hidden behind this tile's work
+            // pull the NEXT tile's g_out rows (contiguous: whole images) into L2 so the pipelined 128-bit loads of
+            // the grad_z warps see L2 latency instead of HBM latency
+            if (tid == 0 && p.g_out && (kTM % HWT) == 0) {
+                const long long nrow0 = (long long)(tile + gridDim.x) * kTM;
+                const long long nrows = min((long long)kTM, p.N - nrow0);
+                const float* src = p.g_out + (size_t)(nrow0 / HWT) * C * D * HWT;
+                const unsigned bytes = (unsigned)((nrows / HWT) * C * D * HWT * sizeof(float));
+                if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+            }
+        }
         if (warp >= 4) {
             // ---- grad_z: warp handles channels ch = (warp-4) + 4*i; lane handles rows 4*lane .. 4*lane+3 -------------
             const int m = lane * 4;

@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""Config-4 microbenchmark sweep (BASELINE.json configs[3]) + config-5 Gaussian branch, on one B200.
+
+For each (N, D, K, C) point: forward (fused argmin+gather+loss), forward+backward, the kernel path taken, achieved
+algorithmic GB/s and the fraction of the measured HBM peak, index parity vs the C oracle on a 4096-row sample.
+Writes a markdown table (default profiles/r1_sweep.md).  CUDA-event timing, 3 warm-ups, inputs larger than L2 or
+L2 flushed between iterations.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ct_vae_b200 as pkg  # noqa: E402
+from ct_vae_b200 import _lib, gaussian  # noqa: E402
+from oracle import c_oracle as CO  # noqa: E402
+
+PEAK = 6549.1
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def time_ms(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        if flush is not None:
+            flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2]
+
+
+def point(N, D, K, C, HW, kind, dev, flush):
+    d = D // C
+    B = N // HW
+    torch.manual_seed(0)
+    m = (pkg.MultipleCodebookVectorQuantizer(K, D, C) if C > 1 else pkg.VectorQuantizerMS(K, D)).to(dev)
+    books = [q.embedding.weight for q in m.quantizers] if C > 1 else [m.embedding.weight]
+    if kind == "trained":
+        for e in books:
+            e.data = torch.randn(K, d, device=dev) * 0.5
+    side = int(HW ** 0.5)
+    z = torch.randn(B, D, side, side, device=dev).requires_grad_(True)
+    g_out = torch.randn(B, C * d, side, side, device=dev)
+    g_loss = torch.ones((), device=dev)
+    used = min(D, (C - 1) + d)
+    fb = 4 * used + 4 * C * d + 8 * C
+    bb = 4 * C * d + 4 * used + 8 * C + 4 * D
+    small = N * D * 4 < 200e6
+    fl = flush if small else None
+
+    def fwd():
+        with torch.no_grad():
+            return m(z, inds=True)
+
+    def fwdbwd():
+        out, loss = m(z)
+        torch.autograd.backward([out, loss], [g_out, g_loss])
+        z.grad = None
+        for e in books:
+            e.grad = None
+
+    iters = 10 if N >= (1 << 22) else 20
+    t_f = time_ms(fwd, iters, fl)
+    path = {1: "simt", 2: "tcgen05"}.get(_lib.last_path(), "?")
+    t_fb = time_ms(fwdbwd, iters, fl)
+    # parity sample vs the C oracle (exact)
+    with torch.no_grad():
+        _, _, inds = m(z[: max(1, 4096 // HW)], inds=True)
+    ref = CO.argmin(z[: max(1, 4096 // HW)].detach().cpu(), [e.detach().cpu() for e in books])
+    ok = bool(torch.equal(inds.cpu().reshape(ref.shape), ref))
+    return dict(N=N, D=D, K=K, C=C, HW=HW, codebook=kind, path=path, fwd_ms=t_f, fwdbwd_ms=t_fb,
+                fwd_Mlat_s=N / t_f / 1e3, fwdbwd_Mlat_s=N / t_fb / 1e3, fwd_gbs=fb * N / t_f / 1e6,
+                fwd_frac=fb * N / t_f / 1e6 / PEAK, fwdbwd_gbs=(fb + bb) * N / t_fb / 1e6,
+                fwdbwd_frac=(fb + bb) * N / t_fb / 1e6 / PEAK, idx_exact=ok)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_sweep.md"))
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    pts = [
+        # (N, D, K, C, HW, codebook)   configs 1-3 at their own batch and at a bandwidth-meaningful batch
+        (64 * 256, 64, 512, 1, 256, "init"), (1 << 20, 64, 512, 1, 256, "init"),           # configs/vq_vae.yaml
+        (64 * 64, 128, 64, 4, 64, "trained"), (1 << 20, 128, 64, 4, 64, "trained"), (1 << 22, 128, 64, 4, 64, "trained"),  # mcq_vae.yaml
+        (16 * 64, 128, 64, 1, 64, "trained"), (1 << 20, 128, 64, 1, 64, "trained"),       # ct_mcq_vae.yaml
+        # config-4 sweep
+        (1 << 16, 32, 256, 1, 256, "trained"), (1 << 20, 32, 256, 1, 256, "trained"), (1 << 22, 32, 256, 1, 256, "trained"),
+        (1 << 20, 64, 256, 1, 256, "trained"), (1 << 20, 128, 256, 1, 256, "trained"), (1 << 18, 256, 256, 1, 256, "trained"),
+        (1 << 20, 64, 1024, 1, 256, "trained"), (1 << 18, 128, 4096, 1, 256, "trained"), (1 << 16, 256, 16384, 1, 256, "trained"),
+    ]
+    if not args.quick:
+        pts += [(1 << 24, 32, 256, 1, 256, "trained")]
+    rows = []
+    for pt in pts:
+        try:
+            r = point(*pt, dev, flush)
+        except RuntimeError as e:
+            r = dict(N=pt[0], D=pt[1], K=pt[2], C=pt[3], HW=pt[4], codebook=pt[5], error=str(e)[:80])
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+    # config 5: reparam + KL
+    g = []
+    for B, L in ((4096, 128), (1 << 17, 128)):
+        mu = torch.randn(B, L, device=dev, requires_grad=True)
+        lv = (torch.randn(B, L, device=dev) * 0.5).requires_grad_(True)
+        eps = torch.randn(B, L, device=dev)
+        gz = torch.randn(B, L, device=dev)
+        gk = torch.ones((), device=dev)
+        fl = flush if B * L * 16 < 200e6 else None
+
+        def f():
+            with torch.no_grad():
+                return gaussian.reparam_kld(mu, lv, eps)
+
+        def fb():
+            zz, kk = gaussian.reparam_kld(mu, lv, eps)
+            torch.autograd.backward([zz, kk], [gz, gk])
+            mu.grad = None
+            lv.grad = None
+
+        tf_, tfb = time_ms(f, 20, fl), time_ms(fb, 20, fl)
+        r = dict(B=B, L=L, fwd_ms=tf_, fwdbwd_ms=tfb, fwd_gbs=16 * B * L / tf_ / 1e6, fwd_frac=16 * B * L / tf_ / 1e6 / PEAK,
+                 fwdbwd_gbs=(16 + 24) * B * L / tfb / 1e6, fwdbwd_frac=(16 + 24) * B * L / tfb / 1e6 / PEAK)
+        g.append(r)
+        print(json.dumps(r), flush=True)
+    with open(args.out, "w") as f:
+        f.write("# round 1 — quantiser microbenchmark sweep (BASELINE.json configs[3]) and Gaussian branch (configs[4])\n\n")
+        f.write(f"One B200, fp32, CUDA-event median, HBM peak {PEAK:.0f} GB/s (MEASURED_PEAKS.json). `frac` = algorithmic bytes ÷ time ÷ peak "
+                "(HBM roofline; points with K ≥ 1024 are bound by the SIMT FFMA rate / epilogue issue, not HBM — next round). "
+                "`idx_exact` = indices equal to the C oracle on a 4096-row sample.\n\n")
+        f.write("| N | D | K | C | HW | codebook | path | fwd ms | fwd M lat/s | fwd GB/s | fwd frac | fwd+bwd ms | fwd+bwd M lat/s | fwd+bwd GB/s | fwd+bwd frac | idx_exact |\n")
+        f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        for r in rows:
+            if "error" in r:
+                f.write(f"| {r['N']} | {r['D']} | {r['K']} | {r['C']} | {r['HW']} | {r['codebook']} | error: {r['error']} |\n")
+                continue
+            f.write(f"| {r['N']} | {r['D']} | {r['K']} | {r['C']} | {r['HW']} | {r['codebook']} | {r['path']} | {r['fwd_ms']:.4f} | "
+                    f"{r['fwd_Mlat_s']:.1f} | {r['fwd_gbs']:.0f} | {r['fwd_frac']:.3f} | {r['fwdbwd_ms']:.4f} | {r['fwdbwd_Mlat_s']:.1f} | "
+                    f"{r['fwdbwd_gbs']:.0f} | {r['fwdbwd_frac']:.3f} | {r['idx_exact']} |\n")
+        f.write("\n## reparameterise + KL (16 B/element forward: mu, logvar, eps in, z out; backward +24 B)\n\n")
+        f.write("| B | L | fwd ms | fwd GB/s | fwd frac | fwd+bwd ms | fwd+bwd GB/s | fwd+bwd frac |\n|---|---|---|---|---|---|---|---|\n")
+        for r in g:
+            f.write(f"| {r['B']} | {r['L']} | {r['fwd_ms']:.4f} | {r['fwd_gbs']:.0f} | {r['fwd_frac']:.3f} | {r['fwdbwd_ms']:.4f} | "
+                    f"{r['fwdbwd_gbs']:.0f} | {r['fwdbwd_frac']:.3f} |\n")
+    print("wrote", args.out)
+
+
+if __name__ == "__main__":
+    main()
