@@ -9,6 +9,8 @@
 //   warps 0-3  codebook gradient: each warp owns one (codebook, 32-channel chunk) slab of the shared [C,K,d]
 //              accumulator, lanes along the channel — plain shared-memory read-modify-write, no atomics.
 // All address arithmetic folds into immediates; the accumulator is flushed once per (persistent) CTA.
+#include <stdlib.h>
+
 #include "ctvq_common.cuh"
 
 namespace ctvq {
@@ -209,6 +211,230 @@ int launch(const BwdParams& p, cudaStream_t s) {
     kern<<<grid, kBT, smem, s>>>(p, (int)nt);
     return (int)cudaGetLastError();
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {  // hinted wait, ~2 s bound then trap
+    for (int it = 0; it < 2048; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// One image (H*W = TM rows) per tile, one persistent CTA per SM, 12 warps:
+//   warps 0-3  "acc": register-prefetch the tile's indices + touched z channels one tile ahead, publish them in a
+//              double-buffered shared slot, accumulate the codebook gradient (warp-owned slabs, no atomics);
+//              thread 0 also drives a 3-stage cp.async.bulk (TMA) ring that streams the image's whole g_out block
+//              (C*D x HW fp32, contiguous in NCHW) into shared memory two tiles ahead;
+//   warps 4-11 "gz": grad_z from shared memory only (128-bit LDS of g_out, codeword gathers), 128-bit stores.
+// No global load sits on any warp's critical path, so HBM stays busy with ~2 tiles of reads in flight per SM.
+constexpr int kBT4 = 384;
+template <int D, int C, int K, int HWT, int DTOT, int CS>
+__global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, const int ntiles) {
+    constexpr int TM = HWT;                 // rows per tile = one image
+    constexpr int NST = 3;                  // g_out ring depth
+    constexpr int USED = (C - 1) * CS + D;
+    constexpr int ZS = TM + 1;
+    constexpr int ESD = D + 1;
+    constexpr int CKD = C * K * D;
+    constexpr int JCH = (D + 31) / 32;
+    constexpr int ITEMS = C * JCH;
+    constexpr int GOF = C * D * TM;         // floats per g_out stage
+    constexpr int NGZ = 8;                  // gz warps
+    constexpr int kFull = 1, kEmpty = 3, kAcc = 5;
+    static_assert(ITEMS <= 4 && TM == 64, "configs' shapes");
+    extern __shared__ __align__(128) float smem[];
+    float* go_s = smem;                                   // [NST][C*D][TM]
+    int* idx_s = reinterpret_cast<int*>(go_s + NST * GOF);  // [2][C][TM]
+    float* zs = reinterpret_cast<float*>(idx_s + 2 * C * TM);  // [2][USED][ZS]
+    float* acc = zs + 2 * USED * ZS;                      // [C][K][D]
+    float* es = acc + CKD;                                // [C][K][D+1]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(es + ((C * K * ESD + 1) & ~1));  // full[NST], empty[NST]
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NST]);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, NGZ); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < CKD; i += kBT4) acc[i] = 0.0f;
+    for (int i = tid; i < CKD; i += kBT4) {
+        const int j = i % D, ck = i / D;
+        es[ck * ESD + j] = __ldg(p.E[ck / K] + (size_t)(ck % K) * D + j);
+    }
+    const float gl = __ldg(p.g_loss);
+    const double nd = (double)p.N * (double)D;
+    const float coef_e = (float)(2.0 / nd) * gl;
+    const float coef_z = (float)(2.0 * (double)p.beta / nd) * gl;
+    __syncthreads();
+    const int niter = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool has_go = p.g_out != nullptr;
+
+    if (warp < 4) {
+        // =========================== acc warps ===========================
+        constexpr int NZ = (USED + 1) / 2, NI = (C + 1) / 2;
+        float zreg[NZ];
+        long long kreg[NI];
+        const int m = tid & (TM - 1), half = tid / TM;  // thread stages row m, channels / codebooks of parity `half`
+        auto prefetch = [&](int it) {
+            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;  // tile = image
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int c = half + 2 * i;
+                kreg[i] = (c < C) ? __ldg(p.idx + ((size_t)b * C + c) * HWT + m) : 0;
+            }
+            const float* src = p.z + (size_t)b * DTOT * HWT + m;
+#pragma unroll
+            for (int i = 0; i < NZ; ++i) {
+                const int ch = half + 2 * i;
+                zreg[i] = (ch < USED) ? __ldg(src + (size_t)ch * HWT) : 0.0f;
+            }
+        };
+        auto issue_go = [&](int it) {  // thread 0: stream image it's g_out block into ring slot it % NST
+            const int st = it % NST;
+            if (it >= NST) mbar_wait(bar_empty + 8 * st, (uint32_t)((it / NST) - 1) & 1u);
+            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+            mbar_expect_tx(bar_full + 8 * st, GOF * 4u);
+            bulk_g2s(smem_u32(go_s + st * GOF), p.g_out + (size_t)b * GOF, GOF * 4u, bar_full + 8 * st);
+        };
+        if (niter > 0) prefetch(0);
+        if (tid == 0 && has_go)
+            for (int it = 0; it < NST - 1 && it < niter; ++it) issue_go(it);
+        for (int it = 0; it < niter; ++it) {
+            const int buf = it & 1;
+            if (tid == 0 && has_go && it + NST - 1 < niter) issue_go(it + NST - 1);
+            if (it >= 2) named_sync(kEmpty + buf, kBT4 - 0);  // gz warps finished reading this z/idx slot (iteration it-2)
+            int* idb = idx_s + buf * C * TM;
+            float* zb = zs + buf * USED * ZS;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int c = half + 2 * i;
+                if (c < C) {
+                    long long kk = kreg[i];
+                    if (kk < 0 || kk >= K) { atomicOr(p.err, 1u); kk = kk < 0 ? 0 : K - 1; }
+                    idb[c * TM + m] = (int)kk;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NZ; ++i)
+                if (half + 2 * i < USED) zb[(half + 2 * i) * ZS + m] = zreg[i];
+            named_arrive(kFull + buf, kBT4);
+            named_sync(kAcc, 128);
+            if (it + 1 < niter) prefetch(it + 1);
+            if (warp < ITEMS) {
+                const int c = warp / JCH;
+                const int j = (warp - c * JCH) * 32 + lane;
+                const bool act = j < D;
+                const int jj = act ? j : 0;
+                const float* zcol = zb + (c * CS + jj) * ZS;
+                const int* ks = idb + c * TM;
+                float* ac = acc + c * K * D + jj;
+                const float* ec = es + c * K * ESD + jj;
+#pragma unroll 2
+                for (int r = 0; r < TM; r += 4) {
+                    const int4 kk = *reinterpret_cast<const int4*>(ks + r);
+                    const bool distinct = kk.x != kk.y && kk.x != kk.z && kk.x != kk.w && kk.y != kk.z && kk.y != kk.w &&
+                                          kk.z != kk.w;
+                    if (act) {
+                        const float d0 = __fsub_rn(ec[kk.x * ESD], zcol[r]), d1 = __fsub_rn(ec[kk.y * ESD], zcol[r + 1]);
+                        const float d2 = __fsub_rn(ec[kk.z * ESD], zcol[r + 2]), d3 = __fsub_rn(ec[kk.w * ESD], zcol[r + 3]);
+                        if (distinct) {
+                            const float a0 = ac[kk.x * D], a1 = ac[kk.y * D], a2 = ac[kk.z * D], a3 = ac[kk.w * D];
+                            ac[kk.x * D] = a0 + d0; ac[kk.y * D] = a1 + d1; ac[kk.z * D] = a2 + d2; ac[kk.w * D] = a3 + d3;
+                        } else {
+                            ac[kk.x * D] += d0; ac[kk.y * D] += d1; ac[kk.z * D] += d2; ac[kk.w * D] += d3;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // =========================== gz warps ===========================
+        const int gw = warp - 4;                 // 0..7
+        const int hsel = lane >> 4;              // half-warp: which channel of the pair
+        const int m = (lane & 15) * 4;           // rows m..m+3
+        for (int it = 0; it < niter; ++it) {
+            const int buf = it & 1, st = it % NST;
+            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const int* idb = idx_s + buf * C * TM;
+            const float* zb = zs + buf * USED * ZS;
+            const float* gos = go_s + st * GOF;
+            float* gz_row = p.gz + (size_t)b * DTOT * HWT + m;
+            // zero channels first: they depend on nothing
+            for (int ch = USED + 2 * gw + hsel; ch < DTOT; ch += 2 * NGZ)
+                *reinterpret_cast<float4*>(gz_row + (size_t)ch * HWT) = make_float4(0.f, 0.f, 0.f, 0.f);
+            named_sync(kFull + buf, kBT4);
+            if (has_go) mbar_wait(bar_full + 8 * st, (uint32_t)(it / NST) & 1u);
+            int eb[C][4];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int4 kk = *reinterpret_cast<const int4*>(idb + c * TM + m);
+                eb[c][0] = (c * K + kk.x) * ESD; eb[c][1] = (c * K + kk.y) * ESD;
+                eb[c][2] = (c * K + kk.z) * ESD; eb[c][3] = (c * K + kk.w) * ESD;
+            }
+            for (int ch = 2 * gw + hsel; ch < USED; ch += 2 * NGZ) {
+                const float z0 = zb[ch * ZS + m], z1 = zb[ch * ZS + m + 1], z2 = zb[ch * ZS + m + 2], z3 = zb[ch * ZS + m + 3];
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int j = ch - c * CS;
+                    if (j >= 0 && j < D) {
+                        float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (has_go) go = *reinterpret_cast<const float4*>(gos + (c * D + j) * TM + m);
+                        const float d0 = __fsub_rn(es[eb[c][0] + j], z0), d1 = __fsub_rn(es[eb[c][1] + j], z1);
+                        const float d2 = __fsub_rn(es[eb[c][2] + j], z2), d3 = __fsub_rn(es[eb[c][3] + j], z3);
+                        g.x += go.x - coef_z * d0; g.y += go.y - coef_z * d1;
+                        g.z += go.z - coef_z * d2; g.w += go.w - coef_z * d3;
+                    }
+                }
+                *reinterpret_cast<float4*>(gz_row + (size_t)ch * HWT) = g;
+            }
+            __syncwarp();
+            if (lane == 0 && has_go) mbar_arrive(bar_empty + 8 * st);  // ring slot may be refilled
+            named_arrive(kEmpty + buf, kBT4);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < CKD; i += kBT4) {
+        const float v = acc[i];
+        if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
+    }
+}
+
+template <int D, int C, int K, int HWT, int DTOT, int CS>
+int launch_tma(const BwdParams& p, cudaStream_t s) {
+    constexpr int USED = (C - 1) * CS + D;
+    constexpr size_t smem = sizeof(float) * (3 * (size_t)C * D * HWT + 2 * (size_t)C * HWT + 2 * (size_t)USED * (HWT + 1) +
+                                             (size_t)C * K * D + (((size_t)C * K * (D + 1) + 1) & ~(size_t)1)) + 6 * 8;
+    static_assert(smem <= 227 * 1024, "shared memory");
+    if (p.N % HWT != 0) return CTVQ_E_UNSUPPORTED;
+    const long long nt = p.N / HWT;  // one image per tile
+    if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
+    int grid = 148;
+    if (grid > nt) grid = (int)nt;
+    auto kern = vq_bwd_tma_kernel<D, C, K, HWT, DTOT, CS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, kBT4, smem, s>>>(p, (int)nt);
+    return (int)cudaGetLastError();
+}
 }  // namespace
 
 int launch_backward_fast(const BwdParams& p, cudaStream_t s) {
@@ -216,7 +442,11 @@ int launch_backward_fast(const BwdParams& p, cudaStream_t s) {
                          (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 15) == 0);
     if (!aligned) return CTVQ_E_UNSUPPORTED;
     // configs/mcq_vae.yaml: C=4, d=32, K=64, latents [B,128,8,8], overlapping slices
-    if (p.d == 32 && p.C == 4 && p.K == 64 && p.HW == 64 && p.Dtot == 128 && p.cs == 1) return launch<32, 4, 64, 64, 128, 1>(p, s);
+    if (p.d == 32 && p.C == 4 && p.K == 64 && p.HW == 64 && p.Dtot == 128 && p.cs == 1) {
+        const bool go_ok = p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0;
+        if (go_ok && p.N >= 148 * 64 * 4 && !getenv("CTVQ_BWD_NO_TMA")) return launch_tma<32, 4, 64, 64, 128, 1>(p, s);
+        return launch<32, 4, 64, 64, 128, 1>(p, s);
+    }
     return CTVQ_E_UNSUPPORTED;
 }
 

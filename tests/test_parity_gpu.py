@@ -156,6 +156,7 @@ def test_pair_batching_matches_two_calls(env):
     ("cfg1_trained", 64, 64, 16, 16, 1, 512, "trained"),
     ("cfg2_init", 64, 128, 8, 8, 4, 64, "init"),          # configs/mcq_vae.yaml
     ("cfg2_trained", 256, 128, 8, 8, 4, 64, "trained"),
+    ("cfg2_big_tma_backward", 1024, 128, 8, 8, 4, 64, "trained"),  # large enough for the TMA-ring backward kernel
     ("cfg3_trained", 32, 128, 8, 8, 1, 64, "trained"),    # configs/ct_mcq_vae.yaml (x and y)
     ("sweep_d32_k256", 256, 32, 16, 16, 1, 256, "trained"),
     ("sweep_d128_k1024", 64, 128, 16, 16, 1, 1024, "trained"),
