@@ -257,15 +257,16 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
     constexpr int JCH = (D + 31) / 32;
     constexpr int ITEMS = C * JCH;
     constexpr int GOF = C * D * TM;         // floats per g_out stage
-    constexpr int NGZ = 8;                  // gz warps
+    constexpr int NGZ = 4;                  // gz warps (8..11)
+    constexpr int NACC = 8;                 // acc warps: 2 per accumulator slab (row halves, private copies)
     constexpr int kFull = 1, kEmpty = 3, kAcc = 5;
     static_assert(ITEMS <= 4 && TM == 64, "configs' shapes");
     extern __shared__ __align__(128) float smem[];
     float* go_s = smem;                                   // [NST][C*D][TM]
     int* idx_s = reinterpret_cast<int*>(go_s + NST * GOF);  // [2][C][TM]
     float* zs = reinterpret_cast<float*>(idx_s + 2 * C * TM);  // [2][USED][ZS]
-    float* acc = zs + 2 * USED * ZS;                      // [C][K][D]
-    float* es = acc + CKD;                                // [C][K][D+1]
+    float* acc = zs + 2 * USED * ZS;                      // [2][C][K][D]  (one copy per row half)
+    float* es = acc + 2 * CKD;                            // [C][K][D+1]
     uint64_t* bars = reinterpret_cast<uint64_t*>(es + ((C * K * ESD + 1) & ~1));  // full[NST], empty[NST]
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NST]);
 
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
         for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, NGZ); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < CKD; i += kBT4) acc[i] = 0.0f;
+    for (int i = tid; i < 2 * CKD; i += kBT4) acc[i] = 0.0f;
     for (int i = tid; i < CKD; i += kBT4) {
         const int j = i % D, ck = i / D;
         es[ck * ESD + j] = __ldg(p.E[ck / K] + (size_t)(ck % K) * D + j);
@@ -287,23 +288,23 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
     const int niter = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const bool has_go = p.g_out != nullptr;
 
-    if (warp < 4) {
+    if (warp < NACC) {
         // =========================== acc warps ===========================
-        constexpr int NZ = (USED + 1) / 2, NI = (C + 1) / 2;
+        constexpr int NZ = (USED + 3) / 4, NI = (C + 3) / 4;
         float zreg[NZ];
         long long kreg[NI];
-        const int m = tid & (TM - 1), half = tid / TM;  // thread stages row m, channels / codebooks of parity `half`
+        const int m = tid & (TM - 1), half = tid / TM;  // thread stages row m, channels / codebooks congruent to `half` mod 4
         auto prefetch = [&](int it) {
             const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;  // tile = image
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
-                const int c = half + 2 * i;
+                const int c = half + 4 * i;
                 kreg[i] = (c < C) ? __ldg(p.idx + ((size_t)b * C + c) * HWT + m) : 0;
             }
             const float* src = p.z + (size_t)b * DTOT * HWT + m;
 #pragma unroll
             for (int i = 0; i < NZ; ++i) {
-                const int ch = half + 2 * i;
+                const int ch = half + 4 * i;
                 zreg[i] = (ch < USED) ? __ldg(src + (size_t)ch * HWT) : 0.0f;
             }
         };
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
             float* zb = zs + buf * USED * ZS;
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
-                const int c = half + 2 * i;
+                const int c = half + 4 * i;
                 if (c < C) {
                     long long kk = kreg[i];
                     if (kk < 0 || kk >= K) { atomicOr(p.err, 1u); kk = kk < 0 ? 0 : K - 1; }
@@ -334,40 +335,54 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
             }
 #pragma unroll
             for (int i = 0; i < NZ; ++i)
-                if (half + 2 * i < USED) zb[(half + 2 * i) * ZS + m] = zreg[i];
+                if (half + 4 * i < USED) zb[(half + 4 * i) * ZS + m] = zreg[i];
             named_arrive(kFull + buf, kBT4);
-            named_sync(kAcc, 128);
+            named_sync(kAcc, NACC * 32);
             if (it + 1 < niter) prefetch(it + 1);
-            if (warp < ITEMS) {
-                const int c = warp / JCH;
-                const int j = (warp - c * JCH) * 32 + lane;
+            if ((warp & 3) < ITEMS) {
+                const int item = warp & 3, rh = warp >> 2;  // accumulator slab, row half
+                const int c = item / JCH;
+                const int j = (item - c * JCH) * 32 + lane;
                 const bool act = j < D;
                 const int jj = act ? j : 0;
-                const float* zcol = zb + (c * CS + jj) * ZS;
-                const int* ks = idb + c * TM;
-                float* ac = acc + c * K * D + jj;
+                const float* zcol = zb + (c * CS + jj) * ZS + rh * (TM / 2);
+                const int* ks = idb + c * TM + rh * (TM / 2);
+                float* ac = acc + rh * CKD + c * K * D + jj;
                 const float* ec = es + c * K * ESD + jj;
-#pragma unroll 2
-                for (int r = 0; r < TM; r += 4) {
-                    const int4 kk = *reinterpret_cast<const int4*>(ks + r);
-                    const bool distinct = kk.x != kk.y && kk.x != kk.z && kk.x != kk.w && kk.y != kk.z && kk.y != kk.w &&
-                                          kk.z != kk.w;
+                // software pipeline, two row-groups ahead: the (index -> codeword -> diff) loads of groups g+1, g+2 are
+                // issued before the read-modify-write of group g, so shared-memory latency overlaps instead of chaining
+                auto diffs = [&](const int4& kk, int r) {
+                    return make_float4(__fsub_rn(ec[kk.x * ESD], zcol[r]), __fsub_rn(ec[kk.y * ESD], zcol[r + 1]),
+                                       __fsub_rn(ec[kk.z * ESD], zcol[r + 2]), __fsub_rn(ec[kk.w * ESD], zcol[r + 3]));
+                };
+                constexpr int NG = TM / 8;  // this warp's half of the rows
+                int4 kA = *reinterpret_cast<const int4*>(ks), kB = *reinterpret_cast<const int4*>(ks + 4);
+                float4 dA = diffs(kA, 0), dB = diffs(kB, 4);
+#pragma unroll 4
+                for (int g = 0; g < NG; ++g) {
+                    int4 kC = kB;
+                    float4 dC = dB;
+                    if (g + 2 < NG) {
+                        kC = *reinterpret_cast<const int4*>(ks + (g + 2) * 4);
+                        dC = diffs(kC, (g + 2) * 4);
+                    }
                     if (act) {
-                        const float d0 = __fsub_rn(ec[kk.x * ESD], zcol[r]), d1 = __fsub_rn(ec[kk.y * ESD], zcol[r + 1]);
-                        const float d2 = __fsub_rn(ec[kk.z * ESD], zcol[r + 2]), d3 = __fsub_rn(ec[kk.w * ESD], zcol[r + 3]);
+                        const bool distinct = kA.x != kA.y && kA.x != kA.z && kA.x != kA.w && kA.y != kA.z && kA.y != kA.w &&
+                                              kA.z != kA.w;
                         if (distinct) {
-                            const float a0 = ac[kk.x * D], a1 = ac[kk.y * D], a2 = ac[kk.z * D], a3 = ac[kk.w * D];
-                            ac[kk.x * D] = a0 + d0; ac[kk.y * D] = a1 + d1; ac[kk.z * D] = a2 + d2; ac[kk.w * D] = a3 + d3;
+                            const float a0 = ac[kA.x * D], a1 = ac[kA.y * D], a2 = ac[kA.z * D], a3 = ac[kA.w * D];
+                            ac[kA.x * D] = a0 + dA.x; ac[kA.y * D] = a1 + dA.y; ac[kA.z * D] = a2 + dA.z; ac[kA.w * D] = a3 + dA.w;
                         } else {
-                            ac[kk.x * D] += d0; ac[kk.y * D] += d1; ac[kk.z * D] += d2; ac[kk.w * D] += d3;
+                            ac[kA.x * D] += dA.x; ac[kA.y * D] += dA.y; ac[kA.z * D] += dA.z; ac[kA.w * D] += dA.w;
                         }
                     }
+                    kA = kB; dA = dB; kB = kC; dB = dC;
                 }
             }
         }
     } else {
         // =========================== gz warps ===========================
-        const int gw = warp - 4;                 // 0..7
+        const int gw = warp - NACC;              // 0..3
         const int hsel = lane >> 4;              // half-warp: which channel of the pair
         const int m = (lane & 15) * 4;           // rows m..m+3
         for (int it = 0; it < niter; ++it) {
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
     }
     __syncthreads();
     for (int i = tid; i < CKD; i += kBT4) {
-        const float v = acc[i];
+        const float v = acc[i] + acc[CKD + i];
         if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
     }
 }
@@ -422,7 +437,7 @@ template <int D, int C, int K, int HWT, int DTOT, int CS>
 int launch_tma(const BwdParams& p, cudaStream_t s) {
     constexpr int USED = (C - 1) * CS + D;
     constexpr size_t smem = sizeof(float) * (3 * (size_t)C * D * HWT + 2 * (size_t)C * HWT + 2 * (size_t)USED * (HWT + 1) +
-                                             (size_t)C * K * D + (((size_t)C * K * (D + 1) + 1) & ~(size_t)1)) + 6 * 8;
+                                             2 * (size_t)C * K * D + (((size_t)C * K * (D + 1) + 1) & ~(size_t)1)) + 6 * 8;
     static_assert(smem <= 227 * 1024, "shared memory");
     if (p.N % HWT != 0) return CTVQ_E_UNSUPPORTED;
     const long long nt = p.N / HWT;  // one image per tile
