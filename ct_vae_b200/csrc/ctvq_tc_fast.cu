@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
         int nblk = 0;
 #pragma unroll
         for (int mb = 0; mb < 4; ++mb) nblk += (row0 + 32 * mb < p.N) ? 1 : 0;
-        mbar_expect_tx(bar_full0 + 8 * st, (uint32_t)nblk * kBlk);
+        mbar_expect_tx(bar_full0 + 8 * st, (uint32_t)nblk * (uint32_t)((C - 1) * CS + D) * 128u);
         for (int mb = 0; mb < nblk; ++mb) {
             const long long nb = row0 + 32 * mb;
             const long long bb = nb / HWT;
@@ -369,7 +369,7 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
     constexpr int USEDP = ((C - 1) * CS + D + 7) / 8 * 8;
     constexpr int DJB = (D + 31) / 32;
     Maps maps;
-    if (make_maps(p0, maps, USEDP) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
+    if (make_maps(p0, maps, (C - 1) * CS + D) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;  // rows USED..USEDP-1 of the slab stay unwritten and unread
     constexpr size_t smem = (size_t)NSTAGE * 4 * USEDP * 128 + (size_t)C * DJB * NK * 128 +
                             sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (NSTAGE + C) * 8 + 16 + 1024;
     static_assert(smem <= 113 * 1024, "two CTAs per SM");

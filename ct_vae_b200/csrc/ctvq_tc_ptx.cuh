@@ -21,6 +21,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -34,6 +37,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Hot-path wait: try_wait with a suspend-time hint sleeps in hardware until the phase completes (or ~1 ms
 // passes), so the loop body runs once or twice; 2048 expiries (~2 s) trap instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
     for (int it = 0; it < 2048; ++it) {
         uint32_t ok;
         asm volatile(
@@ -43,6 +47,14 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
             : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
         if (ok) return;
     }
+    __trap();
+}
+// Control-lane wait: tight spin (no sleep hint) so a single producer / MMA lane reacts within a few cycles of the
+// phase flip; ~2 s of polling traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (unsigned it = 0; it < (1u << 28); ++it)
+        if (mbar_try_wait(bar, parity)) return;
     __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
