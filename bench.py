@@ -368,45 +368,58 @@ def bench_train(args, dev, world, rank, comm):
     import torch.distributed as dist
 
     import ct_vae_b200 as pkg
-    from ct_vae_b200.harness import MCQVAEShell, train_step
+    from ct_vae_b200.harness import GraphedTrainer, MCQVAEShell
 
     B = args.train_batch
     torch.manual_seed(1320)
     model = MCQVAEShell(3, 128, 64, [64, 128, 256], 0.25, 64, 4).to(dev)
-    net = model
-    if world > 1:
+    if world == 1:
+        trainer = GraphedTrainer(model, (B, 3, 64, 64), dev, lr=5e-4, world=1)
+    else:
+        # N>1: stock torch DDP (the reference's strategy, run.py:99), eager — collectives are not captured
         from torch.nn.parallel import DistributedDataParallel as DDP
-        net = DDP(model, device_ids=[dev.index])
-        net.loss_function = model.loss_function
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+        from ct_vae_b200.harness import train_step
+
+        class _Eager:
+            graph = None
+
+            def __init__(self):
+                self.net = DDP(model, device_ids=[dev.index])
+                self.net.loss_function = model.loss_function
+                self.opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+
+            def step(self, images):
+                return train_step(self.net, self.opt, images.to(dev, non_blocking=True)).detach()
+
+        trainer = _Eager()
     torch.manual_seed(1320 + rank)
     x = torch.rand(B, 3, 64, 64, device=dev)  # Shapes3D images are in [0,1] after ToTensor (dataset.py:72-75)
-    steps, warm = max(10, args.steps), max(5, args.warmup)
+    steps, warm = max(20, args.steps), max(5, args.warmup)
     for _ in range(warm):
-        train_step(net, opt, x)
+        trainer.step(x)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        train_step(net, opt, x)
+        trainer.step(x)
     e1.record()
     torch.cuda.synchronize(dev)
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t)
-    # e2e: images from pinned host memory each step + loss read back
+    # e2e: images from pinned host memory each step + loss read back to the host (experiment.py:96 .item())
     hx = torch.rand(B, 3, 64, 64).pin_memory()
     for _ in range(2):
-        float(train_step(net, opt, hx.to(dev, non_blocking=True)))
+        float(trainer.step(hx))
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        float(train_step(net, opt, hx.to(dev, non_blocking=True)))
+        float(trainer.step(hx))
     torch.cuda.synchronize(dev)
     te = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
@@ -415,8 +428,9 @@ def bench_train(args, dev, world, rank, comm):
             "batch_per_gpu": B, "steps": steps, "ms_per_step": ms / steps,
             "e2e": {"value": B * world * steps / (float(te) * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": B * 3 * 64 * 64 * 4 * world, "d2h_bytes_per_step": 4 * world},
+            "cuda_graph": trainer.graph is not None,
             "model": "MCQVAEShell = layer structure of models/mcq_vae.py:142-317 (10.1 M params), cuDNN convs, "
-                     "ctvq quantiser, Adam lr 5e-4"}
+                     "ctvq quantiser, Adam lr 5e-4; N=1: whole step (fwd, bwd, Adam) replayed from one CUDA graph; N>1: torch DDP, eager"}
 
 
 if __name__ == "__main__":

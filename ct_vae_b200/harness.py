@@ -82,3 +82,61 @@ def train_step(model: nn.Module, optimizer: torch.optim.Optimizer, images: torch
     losses["loss"].backward()
     optimizer.step()
     return losses["loss"]
+
+
+class GraphedTrainer:
+    """The training step above captured ONCE into a CUDA graph (forward, loss, backward, gradient all-reduce, Adam)
+    and replayed per batch — the 'CUDA streams and graphs instead of a tracing compiler' way to remove the ~700
+    tiny-launch overhead that dominates these 10 M-parameter models.  Possible because the ctvq ops never
+    synchronise or allocate.  Gradients live in one flat buffer (parameters' ``.grad`` are views),
+    so data parallelism is a single in-graph NCCL all-reduce + scale: DDP's averaging semantics (run.py:99)."""
+
+    def __init__(self, model: nn.Module, batch_shape, device, lr: float = 5e-4, world: int = 1, m_n: float = 0.00025):
+        import torch.distributed as dist
+        self.model, self.world, self.m_n = model, world, m_n
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.flat = torch.zeros(sum(p.numel() for p in params), device=device)
+        off = 0
+        for p in params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.opt = torch.optim.Adam(params, lr=lr, capturable=True, foreach=True)
+        self.x = torch.zeros(batch_shape, device=device)
+        self.loss = torch.zeros((), device=device)
+
+        def body():
+            self.flat.zero_()
+            results = model(self.x)
+            loss = model.loss_function(*results, M_N=m_n)["loss"]
+            loss.backward()
+            if world > 1:
+                dist.all_reduce(self.flat)
+                self.flat.mul_(1.0 / world)
+            self.opt.step()
+            self.loss.copy_(loss.detach())
+
+        self._body = body
+        self.graph = None
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self.graph = g
+        except Exception as e:  # capture not possible (e.g. a collective that refuses capture): stay eager, say so
+            self.capture_error = repr(e)[:200]
+            torch.cuda.synchronize(device)
+
+    def step(self, images: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(images, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.loss
