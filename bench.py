@@ -373,25 +373,7 @@ def bench_train(args, dev, world, rank, comm):
     B = args.train_batch
     torch.manual_seed(1320)
     model = MCQVAEShell(3, 128, 64, [64, 128, 256], 0.25, 64, 4).to(dev)
-    if world == 1:
-        trainer = GraphedTrainer(model, (B, 3, 64, 64), dev, lr=5e-4, world=1)
-    else:
-        # N>1: stock torch DDP (the reference's strategy, run.py:99), eager — collectives are not captured
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        from ct_vae_b200.harness import train_step
-
-        class _Eager:
-            graph = None
-
-            def __init__(self):
-                self.net = DDP(model, device_ids=[dev.index])
-                self.net.loss_function = model.loss_function
-                self.opt = torch.optim.Adam(model.parameters(), lr=5e-4)
-
-            def step(self, images):
-                return train_step(self.net, self.opt, images.to(dev, non_blocking=True)).detach()
-
-        trainer = _Eager()
+    trainer = GraphedTrainer(model, (B, 3, 64, 64), dev, lr=5e-4, world=world)
     torch.manual_seed(1320 + rank)
     x = torch.rand(B, 3, 64, 64, device=dev)  # Shapes3D images are in [0,1] after ToTensor (dataset.py:72-75)
     steps, warm = max(20, args.steps), max(5, args.warmup)
@@ -430,7 +412,7 @@ def bench_train(args, dev, world, rank, comm):
                     "h2d_bytes_per_step": B * 3 * 64 * 64 * 4 * world, "d2h_bytes_per_step": 4 * world},
             "cuda_graph": trainer.graph is not None,
             "model": "MCQVAEShell = layer structure of models/mcq_vae.py:142-317 (10.1 M params), cuDNN convs, "
-                     "ctvq quantiser, Adam lr 5e-4; N=1: whole step (fwd, bwd, Adam) replayed from one CUDA graph; N>1: torch DDP, eager"}
+                     "ctvq quantiser, Adam lr 5e-4; step replayed from two CUDA graphs (fwd+bwd, Adam) with one eager NCCL all-reduce of the flat gradient between them for N>1"}
 
 
 if __name__ == "__main__":

@@ -85,14 +85,14 @@ def train_step(model: nn.Module, optimizer: torch.optim.Optimizer, images: torch
 
 
 class GraphedTrainer:
-    """The training step above captured ONCE into a CUDA graph (forward, loss, backward, gradient all-reduce, Adam)
-    and replayed per batch — the 'CUDA streams and graphs instead of a tracing compiler' way to remove the ~700
-    tiny-launch overhead that dominates these 10 M-parameter models.  Possible because the ctvq ops never
-    synchronise or allocate.  Gradients live in one flat buffer (parameters' ``.grad`` are views),
-    so data parallelism is a single in-graph NCCL all-reduce + scale: DDP's averaging semantics (run.py:99)."""
+    """The training step above captured into CUDA graphs and replayed per batch — the 'CUDA streams and graphs instead
+    of a tracing compiler' way to remove the ~700 tiny-launch overhead that dominates these 10 M-parameter models.
+    Possible because the ctvq ops never synchronise or allocate.  Two graphs: (A) zero-grad, forward,
+    loss, backward; (B) Adam.  Gradients live in ONE flat buffer (parameters' ``.grad`` are views), so data
+    parallelism is a single eager NCCL all-reduce + scale between the two replays: DDP's averaging semantics
+    (run.py:99) without DDP's per-bucket hooks.  Collectives are deliberately NOT captured."""
 
     def __init__(self, model: nn.Module, batch_shape, device, lr: float = 5e-4, world: int = 1, m_n: float = 0.00025):
-        import torch.distributed as dist
         self.model, self.world, self.m_n = model, world, m_n
         params = [p for p in model.parameters() if p.requires_grad]
         self.flat = torch.zeros(sum(p.numel() for p in params), device=device)
@@ -104,32 +104,32 @@ class GraphedTrainer:
         self.x = torch.zeros(batch_shape, device=device)
         self.loss = torch.zeros((), device=device)
 
-        def body():
+        def fwd_bwd():
             self.flat.zero_()
             results = model(self.x)
             loss = model.loss_function(*results, M_N=m_n)["loss"]
             loss.backward()
-            if world > 1:
-                dist.all_reduce(self.flat)
-                self.flat.mul_(1.0 / world)
-            self.opt.step()
             self.loss.copy_(loss.detach())
 
-        self._body = body
-        self.graph = None
+        self._fwd_bwd = fwd_bwd
+        self.graph = self.graph_opt = None
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(3):
-                body()
+                fwd_bwd()
+                self.opt.step()
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                body()
-            self.graph = g
-        except Exception as e:  # capture not possible (e.g. a collective that refuses capture): stay eager, say so
+                fwd_bwd()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self.opt.step()
+            self.graph, self.graph_opt = g, g2
+        except Exception as e:  # capture not possible: stay eager, say so
             self.capture_error = repr(e)[:200]
             torch.cuda.synchronize(device)
 
@@ -138,5 +138,13 @@ class GraphedTrainer:
         if self.graph is not None:
             self.graph.replay()
         else:
-            self._body()
+            self._fwd_bwd()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat)
+            self.flat.mul_(1.0 / self.world)
+        if self.graph_opt is not None:
+            self.graph_opt.replay()
+        else:
+            self.opt.step()
         return self.loss
