@@ -67,7 +67,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -332,11 +332,15 @@ def main():
         {"kernel": "vq_backward (grad_z + codebook scatter-add)", "ms": bwd_ms, "alg_bytes": bb * rows_per_gpu,
          "gbs": bb * rows_per_gpu / (bwd_ms * 1e-3) / 1e9},
     ]
-    for k in kernels:
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full capture
+    # of this very workload (profiles/r1_final_b16384.md); only quoted for the profiled batch size
+    ncu_traffic = {16384: (146977792 + 511628032, 717342720 + 497072128)}.get(B)
+    for i, k in enumerate(kernels):
         k["frac"] = k["gbs"] / peak
+        k["traffic"] = ncu_traffic[i] if ncu_traffic else None
     dom = max(kernels, key=lambda k: k["ms"])
     roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": None, "kernel": dom["kernel"], "peak_source": peak_src,
+                "traffic": dom["traffic"], "kernel": dom["kernel"], "peak_source": peak_src,
                 "alg_bytes_per_latent": {"fwd": fb, "bwd": bb}}
 
     train = None
