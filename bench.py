@@ -201,6 +201,7 @@ def main():
     from ct_vae_b200 import _lib
     from ct_vae_b200.dist import CodebookGradComm
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the ONE JSON line (NCCL banners go to stderr)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
