@@ -35,6 +35,28 @@ METRIC = "quantised_latents_per_sec_fwd_bwd"
 UNIT = "latents/s"
 
 
+_JSON_FD = None
+
+
+def _quiet_stdout():
+    """Route fd 1 to stderr for the whole run (NCCL / cuDNN banners are written by C code straight to fd 1) and keep
+    a private duplicate for the ONE JSON line the driver parses."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -162,7 +184,7 @@ def run_reference_arm(args):
                              "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(batch_per_gpu, n_gpus):
@@ -201,7 +223,7 @@ def main():
     from ct_vae_b200 import _lib
     from ct_vae_b200.dist import CodebookGradComm
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the ONE JSON line (NCCL banners go to stderr)
+    _quiet_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -359,7 +381,7 @@ def main():
                         "d2h_bytes_per_step": 4 * world, "steps": e2e_steps},
                 "gpu_launches": (2 + (2 if world > 1 else 0)) * args.steps,
                 "roofline": roofline, "kernels": kernels, "clocks": clocks, "cpu_baseline": cpu, "train": train}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         if comm is not None:
             comm.close()
