@@ -26,8 +26,8 @@ __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("
 // shared-memory slot (register prefetch one tile ahead) and run the codebook-gradient accumulation; warps 4-7 ("gz")
 // run grad_z with a 2-deep software pipeline of 128-bit g_out loads.  The two halves only meet at named barriers
 // FULL[buf] / EMPTY[buf], so neither waits for the other inside a tile.
-template <int D, int C, int K, int HWT, int DTOT, int CS>
-__global__ void __launch_bounds__(kBT, 2) vq_bwd_fast_kernel(const BwdParams p, const int ntiles) {
+template <int D, int C, int K, int HWT, int DTOT, int CS, int MINB>
+__global__ void __launch_bounds__(kBT, MINB) vq_bwd_fast_kernel(const BwdParams p, const int ntiles) {
     constexpr int USED = (C - 1) * CS + D;
     constexpr int ZS = kTM + 1;
     constexpr int ESD = D + 1;
@@ -195,17 +195,17 @@ __global__ void __launch_bounds__(kBT, 2) vq_bwd_fast_kernel(const BwdParams p, 
     }
 }
 
-template <int D, int C, int K, int HWT, int DTOT, int CS>
+template <int D, int C, int K, int HWT, int DTOT, int CS, int MINB>
 int launch(const BwdParams& p, cudaStream_t s) {
     constexpr int USED = (C - 1) * CS + D;
     constexpr size_t smem = sizeof(float) * (2 * (size_t)C * kTM + 2 * (size_t)USED * (kTM + 1) + (size_t)C * K * D + (size_t)C * K * (D + 1));
-    static_assert(smem <= 113 * 1024, "two CTAs per SM");
+    static_assert(smem <= (MINB == 2 ? 113 : 225) * 1024, "shared memory budget");
     const long long nt = (p.N + kTM - 1) / kTM;
     if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
-    int grid = 148 * 2;
+    int grid = 148 * MINB;
     if (grid > nt) grid = (int)nt;
     if (grid < 1) grid = 1;
-    auto kern = vq_bwd_fast_kernel<D, C, K, HWT, DTOT, CS>;
+    auto kern = vq_bwd_fast_kernel<D, C, K, HWT, DTOT, CS, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kBT, smem, s>>>(p, (int)nt);
@@ -460,8 +460,10 @@ int launch_backward_fast(const BwdParams& p, cudaStream_t s) {
     if (p.d == 32 && p.C == 4 && p.K == 64 && p.HW == 64 && p.Dtot == 128 && p.cs == 1) {
         const bool go_ok = p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0;
         if (go_ok && p.N >= 148 * 64 * 4 && !getenv("CTVQ_BWD_NO_TMA")) return launch_tma<32, 4, 64, 64, 128, 1>(p, s);
-        return launch<32, 4, 64, 64, 128, 1>(p, s);
+        return launch<32, 4, 64, 64, 128, 1, 2>(p, s);
     }
+    // configs/ct_mcq_vae.yaml: C=1, d=128, K=64, latents [B,128,8,8]
+    if (p.d == 128 && p.C == 1 && p.K == 64 && p.HW == 64 && p.Dtot == 128) return launch<128, 1, 64, 64, 128, 1, 1>(p, s);
     return CTVQ_E_UNSUPPORTED;
 }
 

@@ -76,5 +76,6 @@ int launch_reparam_bwd(const float* mu, const float* lv, const float* eps, const
 int launch_forward_tc(const QuantParams& p, cudaStream_t s);  // returns CTVQ_E_UNSUPPORTED when shape not covered
 bool tc_supported(const QuantParams& p);
 int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s);  // shape-specialised tcgen05 kernels
+int launch_forward_tc_c1(const QuantParams& p, cudaStream_t s);    // single-codebook row-split tcgen05 kernels
 
 }  // namespace ctvq

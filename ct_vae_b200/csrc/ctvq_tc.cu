@@ -381,7 +381,9 @@ bool tc_supported(const QuantParams& p) { return make_plan(p).ok; }
 
 int launch_forward_tc(const QuantParams& p0, cudaStream_t s) {
     if (!g_dbg) {
-        const int rc = launch_forward_tc_fast(p0, s);
+        int rc = launch_forward_tc_fast(p0, s);
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
+        rc = launch_forward_tc_c1(p0, s);
         if (rc != CTVQ_E_UNSUPPORTED) return rc;
     }
     const Plan pl = make_plan(p0);

@@ -392,8 +392,6 @@ int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
     if (!encode_fn()) return CTVQ_E_UNSUPPORTED;
     // configs/mcq_vae.yaml: C=4 codebooks x d=32 on overlapping slices of [B,128,8,8]
     if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) return launch_fast<32, 64, 64, 4, 1, 3>(p, s);
-    // configs/ct_mcq_vae.yaml: C=1, d=128
-    if (p.d == 128 && p.HW == 64 && p.C == 1) return launch_fast<128, 64, 64, 1, 1, 1>(p, s);
     return CTVQ_E_UNSUPPORTED;
 }
 
