@@ -22,9 +22,17 @@ def _shape(latents: Tensor, codebooks: Sequence[Tensor], chan_stride: int):
     if (c - 1) * chan_stride + d > dtot:
         # same failure class as the reference: a size mismatch inside torch.matmul (models/mcq_vae.py:33)
         raise RuntimeError(f"codebook slices ({c} x {d} channels, stride {chan_stride}) exceed the {dtot} latent channels")
-    if latents.dtype != torch.float32:
-        raise RuntimeError(f"latents must be float32 (the reference's arithmetic type), got {latents.dtype}")
+    if latents.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"latents must be float32 (the reference's arithmetic type) or bfloat16, got {latents.dtype}")
     return b, dtot, h, w, c, d, k
+
+
+def _bf16_operands(z: Tensor, es: Sequence[Tensor]):
+    """bf16 mode (not defined by the reference — `.bfloat16()` raises at models/vq_vae.py:43): the fp32 contract
+    applied to bf16-ROUNDED latents and codebooks.  bf16 values are exact in fp32, so the kernels run
+    unchanged on up-cast copies; outputs are rounded to bf16 by the caller.  (Native bf16 tiles, which would halve
+    the HBM bytes, are next-round work: today this mode costs extra cast passes.)"""
+    return z.float(), [e.to(torch.bfloat16).float() for e in es]
 
 
 def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], chan_stride: int = 1) -> List[Tensor]:
@@ -35,6 +43,12 @@ def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], ch
     zs = [z.detach().contiguous() for z in latents_list]
     es = [e.detach() for e in codebooks]
     b, dtot, h, w, c, d, k = _shape(zs[0], es, chan_stride)
+    if zs[0].dtype == torch.bfloat16:
+        zs32 = []
+        for z in zs:
+            z32, es = _bf16_operands(z, [e.detach() for e in codebooks])
+            zs32.append(z32)
+        zs = zs32
     for z in zs[1:]:
         if z.shape != zs[0].shape:
             raise RuntimeError("paired inputs must share a shape")
@@ -57,6 +71,9 @@ class _Quantize(torch.autograd.Function):
         z = latents.detach().contiguous()
         es = [e.detach() for e in codebooks]
         b, dtot, h, w, c, d, k = _shape(z, es, chan_stride)
+        io_dtype = z.dtype
+        if io_dtype == torch.bfloat16:
+            z, es = _bf16_operands(z, es)
         dev = z.device
         out = torch.empty((b, c * d, h, w), dtype=z.dtype, device=dev)
         losses = torch.empty(c + 1, dtype=torch.float32, device=dev)
@@ -80,6 +97,9 @@ class _Quantize(torch.autograd.Function):
             _lib.check(rc, "ctvq_gather_st_loss")
         ctx.save_for_backward(z, inds, *es)
         ctx.meta = (float(beta), int(chan_stride), b, dtot, h, w, c, d, k, comm)
+        ctx.io_dtype = io_dtype
+        if io_dtype == torch.bfloat16:
+            out = out.to(torch.bfloat16)
         per = losses[:c]
         ctx.mark_non_differentiable(inds, per)
         ctx.set_materialize_grads(False)  # unused outputs arrive as None: no zero-fill kernels, no host sync
@@ -95,7 +115,7 @@ class _Quantize(torch.autograd.Function):
         g_loss = g_loss.to(torch.float32).contiguous()
         go_ptr = None
         if g_out is not None:
-            g_out = g_out.contiguous()
+            g_out = g_out.contiguous().float()
             go_ptr = g_out.data_ptr()
         gz = torch.empty_like(z)
         ge = torch.empty((c, k, d), dtype=torch.float32, device=dev)
@@ -107,6 +127,8 @@ class _Quantize(torch.autograd.Function):
         _lib.check(rc, "ctvq_backward")
         if comm is not None:
             comm.allreduce_(ge)  # the one collective of the path, on the backward kernel's stream
+        if ctx.io_dtype == torch.bfloat16:
+            gz = gz.to(torch.bfloat16)
         return (gz, None, None, None, None, *ge.unbind(0))
 
 

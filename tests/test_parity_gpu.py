@@ -323,3 +323,38 @@ def test_cpu_tensor_raises(env):
     m = pkg.VectorQuantizer(8, 4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.randn(2, 4, 3, 3))
+
+
+def test_bf16_mode_is_the_fp32_contract_on_rounded_operands(env):
+    """bf16 is undefined in the reference (models/vq_vae.py:43 raises); we define it as the fp32 arithmetic applied
+    to bf16-rounded latents and codebooks, outputs rounded to bf16.  Indices: exact vs the C oracle on the rounded
+    operands; loss: 1e-5 vs the oracle on rounded operands, 2e-2 (north_star's bf16 tolerance) vs the fp32 result."""
+    pkg, _lib, O, CO = env
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    B, D, H, W, C, K = 64, 128, 8, 8, 4, 64
+    d = D // C
+    m = pkg.MultipleCodebookVectorQuantizer(K, D, C, 0.25)
+    for q in m.quantizers:
+        q.embedding.weight.data = torch.randn(K, d) * 0.5
+    books = [q.embedding.weight.detach().clone() for q in m.quantizers]
+    z32 = torch.randn(B, D, H, W)
+    m = m.to(dev)
+    zb = z32.to(dev).to(torch.bfloat16).requires_grad_(True)
+    out, loss, inds = m(zb, inds=True)
+    assert out.dtype == torch.bfloat16 and inds.dtype == torch.int64
+    zr = zb.detach().float().cpu()
+    er = [e.to(torch.bfloat16).float() for e in books]
+    assert torch.equal(inds.cpu(), CO.argmin(zr, er))
+    ref_out, ref_loss, _ = O.mcq_compute_latents(zr, inds.cpu(), er, 0.25)
+    assert torch.equal(out.detach().float().cpu(), ref_out.to(torch.bfloat16).float())
+    assert rel_err(loss.detach().cpu(), ref_loss) < TOL
+    _, fp32_loss, _, _ = O.mcq_forward(z32, books, 0.25)
+    assert abs(float(loss) - float(fp32_loss)) < 2e-2 * abs(float(fp32_loss))
+    g_out = torch.randn(B, D, H, W)
+    (out.float() * g_out.to(dev)).sum().add(0.7 * loss).backward()
+    gz, ges = O.mcq_backward(zr, inds.cpu(), er, 0.25, g_out, torch.tensor(0.7))
+    assert zb.grad.dtype == torch.bfloat16
+    assert rel_err(zb.grad.float().cpu(), gz) < 2e-2
+    for q, ge in zip(m.quantizers, ges):
+        assert rel_err(q.embedding.weight.grad.cpu(), ge) < TOL
