@@ -155,6 +155,50 @@ def cpu_baseline(budget_s=12.0, batch=1024, max_reps=20):
                       f"latents, best of {len(times)} reps", "ms_per_sample": best * 1e3}
 
 
+def torch_eager_gpu_baseline(dev, batch=4096, reps=5):
+    """The reference's op sequence (models/mcq_vae.py:26-64,100-127: permute, matmul distances, argmin, one-hot scatter,
+    one-hot matmul, two mse_loss, straight-through, permute back; autograd backward) as STOCK torch eager on the same
+    B200 — the honest GPU baseline the fused kernels replace.  Plain library calls, none of our kernels."""
+    import torch.nn.functional as F
+    C, K, D, H, W = (CFG[k] for k in "CKDHW")
+    d = D // C
+    torch.manual_seed(1320)
+    books = [(torch.randn(K, d, device=dev) * 0.5).requires_grad_(True) for _ in range(C)]
+    z = torch.randn(batch, D, H, W, device=dev, requires_grad=True)
+    g_out = torch.randn(batch, D, H, W, device=dev)
+
+    def step():
+        outs, total = [], 0
+        for i, e in enumerate(books):
+            lat = z[:, i:i + d].permute(0, 2, 3, 1).contiguous()
+            flat = lat.view(-1, d)
+            dist = torch.sum(flat ** 2, dim=1, keepdim=True) + torch.sum(e ** 2, dim=1) - 2 * torch.matmul(flat, e.t())
+            inds = torch.argmin(dist, dim=1).unsqueeze(1)
+            one_hot = torch.zeros(inds.size(0), K, device=dev)
+            one_hot.scatter_(1, inds, 1)
+            q = torch.matmul(one_hot, e).view(lat.shape)
+            total = total + F.mse_loss(q.detach(), lat) * CFG["beta"] + F.mse_loss(q, lat.detach())
+            outs.append((lat + (q - lat).detach()).permute(0, 3, 1, 2).contiguous())
+        out = torch.cat(outs, 1)
+        torch.autograd.backward([out, total], [g_out, torch.ones((), device=dev)])
+        z.grad = None
+        for e in books:
+            e.grad = None
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": batch * H * W / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": batch,
+            "what": "reference op sequence in stock torch eager (fp32, TF32 off) on this GPU"}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path, all host threads, same metric/unit."""
     rank = int(os.environ.get("RANK", "0"))
@@ -370,8 +414,10 @@ def main():
     if not args.no_train:
         train = bench_train(args, dev, world, rank, comm)
     cpu = None
+    eager = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline()
+        eager = torch_eager_gpu_baseline(dev)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -380,7 +426,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * D * H * W * 4 * world,
                         "d2h_bytes_per_step": 4 * world, "steps": e2e_steps},
                 "gpu_launches": (2 + (2 if world > 1 else 0)) * args.steps,
-                "roofline": roofline, "kernels": kernels, "clocks": clocks, "cpu_baseline": cpu, "train": train}
+                "roofline": roofline, "kernels": kernels, "clocks": clocks, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "train": train}
         emit(line)
     if world > 1:
         if comm is not None:
