@@ -254,6 +254,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16384, help="images per GPU per step (x64 latents each)")
     ap.add_argument("--ref-batch", type=int, default=1024)
     ap.add_argument("--train-batch", type=int, default=64, help="MCQ-VAE train-step images per GPU (configs/mcq_vae.yaml:15)")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: one-shot NVLink peer-memory all-reduce of grad_E (default) or NCCL")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -265,7 +267,7 @@ def main():
 
     import ct_vae_b200 as pkg
     from ct_vae_b200 import _lib
-    from ct_vae_b200.dist import CodebookGradComm
+    from ct_vae_b200.dist import CodebookGradComm, PeerGradComm
 
     _quiet_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -279,7 +281,15 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-        comm = CodebookGradComm(device=dev)
+        collective = args.collective
+        if collective == "peer":
+            try:
+                comm = PeerGradComm(CFG["C"] * CFG["K"] * (CFG["D"] // CFG["C"]), dev)
+            except Exception as e:  # no CUDA IPC / peer access on this box: NCCL carries the collective instead
+                print(f"[bench] peer collective unavailable ({e!r}); using NCCL", file=sys.stderr)
+                collective = "nccl"
+        if collective == "nccl":
+            comm = CodebookGradComm(device=dev)
     _lib.lib()
 
     C, K, D, H, W = (CFG[k] for k in "CKDHW")
@@ -422,10 +432,11 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload_config(B, world), collective=(type(comm).__name__ if comm is not None else "none")),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * D * H * W * 4 * world,
                         "d2h_bytes_per_step": 4 * world, "steps": e2e_steps},
-                "gpu_launches": (2 + (2 if world > 1 else 0)) * args.steps,
+                "gpu_launches": (2 + (1 if world > 1 else 0)) * args.steps,
                 "roofline": roofline, "kernels": kernels, "clocks": clocks, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "train": train}
         emit(line)
     if world > 1:

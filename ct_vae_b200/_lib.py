@@ -32,6 +32,14 @@ _SIGNATURES = {
     "ctvq_nccl_comm_init": (_i, [ctypes.POINTER(_vp), _i, _i, _vp, _i]),
     "ctvq_nccl_comm_destroy": (_i, [_vp]),
     "ctvq_allreduce_codebook_grad": (_i, [_vp, _vp, _sz, _f, _i, _vp]),
+    "ctvq_peer_buffer_bytes": (_sz, [_sz, _i]),
+    "ctvq_peer_alloc": (_i, [ctypes.POINTER(_vp), _sz, _i, _i]),
+    "ctvq_peer_free": (_i, [_vp, _i]),
+    "ctvq_peer_export": (_i, [_vp, _vp, _i]),
+    "ctvq_peer_import": (_i, [_vp, ctypes.POINTER(_vp), _i]),
+    "ctvq_peer_close": (_i, [_vp, _i]),
+    "ctvq_peer_slot": (_vp, [_vp, _sz, ctypes.c_uint]),
+    "ctvq_peer_allreduce": (_i, [_vp, _i, _i, _sz, _sz, ctypes.c_uint, _f, _vp, _i, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

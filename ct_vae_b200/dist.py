@@ -77,6 +77,85 @@ class CodebookGradComm:
             self._comm = None
 
 
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ carrier so torch can alias memory the C library allocated."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerGradComm:
+    """The same collective WITHOUT NCCL: a one-shot all-reduce over NVLink peer memory (ctvq_peer_* in include/ctvq.h).
+
+    The backward kernel writes grad_E straight into this rank's symmetric slot (`grad_buffer`); `allreduce_` launches
+    ONE kernel that handshakes through flag words in the peers' buffers and sums the `world` slots in rank order
+    (bit-identical on every rank), scaled by 1/world.  torch.distributed only carries the 64-byte IPC handles.
+    Single node, world <= 8 (every GPU reaches every peer through NVSwitch)."""
+
+    def __init__(self, count_max: int, device: torch.device, group=None, average: bool = True):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (it carries the IPC handles)")
+        self.group, self.device = group, device
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("PeerGradComm covers one NVSwitch box (world <= 8)")
+        self.scale = 1.0 / self.world if average else 1.0
+        self.count_max = int(count_max)
+        self.epoch = 0
+        self.launches = 0
+        L = _lib.lib()
+        own = ctypes.c_void_p()
+        _lib.check(L.ctvq_peer_alloc(ctypes.byref(own), self.count_max, self.world, device.index), "ctvq_peer_alloc")
+        self._own = own
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(L.ctvq_peer_export(own, handle, device.index), "ctvq_peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self._peers = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self._peers.append(own)
+            else:
+                ptr = ctypes.c_void_p()
+                _lib.check(L.ctvq_peer_import(ctypes.create_string_buffer(h, 64), ctypes.byref(ptr), device.index),
+                           "ctvq_peer_import")
+                self._peers.append(ptr)
+        self._table = (ctypes.c_void_p * self.world)(*[p.value for p in self._peers])
+        dist.barrier(group=group)  # every rank has mapped every buffer before anyone signals
+
+    def grad_buffer(self, shape) -> torch.Tensor:
+        """Tensor aliasing the slot the NEXT all-reduce will read (the backward kernel's gE_out)."""
+        n = 1
+        for s in shape:
+            n *= int(s)
+        if n > self.count_max:
+            raise RuntimeError(f"codebook gradient ({n} floats) exceeds the symmetric buffer ({self.count_max})")
+        slot = _lib.lib().ctvq_peer_slot(self._own, self.count_max, self.epoch + 1)
+        return torch.as_tensor(_DeviceArray(slot, n), device=self.device).view(*shape)
+
+    def allreduce_(self, grad: torch.Tensor) -> torch.Tensor:
+        self.epoch += 1
+        out = torch.empty(grad.shape, dtype=torch.float32, device=self.device)
+        rc = _lib.lib().ctvq_peer_allreduce(self._table, self.world, self.rank, self.count_max, grad.numel(),
+                                            self.epoch, self.scale, out.data_ptr(), self.device.index,
+                                            _lib.stream_ptr(self.device))
+        _lib.check(rc, "ctvq_peer_allreduce")
+        self.launches += 1
+        return out
+
+    def close(self):
+        L = _lib.lib()
+        torch.cuda.synchronize(self.device)
+        for r, p in enumerate(self._peers):
+            if r != self.rank and p is not None:
+                L.ctvq_peer_close(p, self.device.index)
+        if self._own is not None:
+            L.ctvq_peer_free(self._own, self.device.index)
+        self._peers, self._own = [], None
+
+
 def shard_batch(global_batch: int, world: int, rank: int):
     """Contiguous even split of the batch dimension (DistributedSampler-style, datasets/transition.py:173-176);
     the remainder goes to the lowest ranks.  -> (start, stop)."""

@@ -118,7 +118,10 @@ class _Quantize(torch.autograd.Function):
             g_out = g_out.contiguous().float()
             go_ptr = g_out.data_ptr()
         gz = torch.empty_like(z)
-        ge = torch.empty((c, k, d), dtype=torch.float32, device=dev)
+        if comm is not None and hasattr(comm, "grad_buffer"):
+            ge = comm.grad_buffer((c, k, d))  # symmetric NVLink-mapped slot: the kernel writes where peers read
+        else:
+            ge = torch.empty((c, k, d), dtype=torch.float32, device=dev)
         sp = _lib.stream_ptr(dev)
         ws = _lib.workspace(dev, sp)
         rc = _lib.lib().ctvq_backward(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), go_ptr, g_loss.data_ptr(), b,
@@ -126,7 +129,7 @@ class _Quantize(torch.autograd.Function):
                                       ws.data_ptr(), ws.numel(), dev.index, sp)
         _lib.check(rc, "ctvq_backward")
         if comm is not None:
-            comm.allreduce_(ge)  # the one collective of the path, on the backward kernel's stream
+            ge = comm.allreduce_(ge)  # the one collective of the path, on the backward kernel's stream
         if ctx.io_dtype == torch.bfloat16:
             gz = gz.to(torch.bfloat16)
         return (gz, None, None, None, None, *ge.unbind(0))

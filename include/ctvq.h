@@ -120,6 +120,26 @@ int ctvq_nccl_comm_destroy(void* comm);
 /* sum over ranks then multiply by `scale` (1/world = DDP's gradient averaging), in place, on `stream`. */
 int ctvq_allreduce_codebook_grad(void* comm, float* gE, size_t count, float scale, int device, void* stream);
 
+/* One-shot all-reduce of the codebook gradient over NVLink peer memory (no NCCL on the path): every rank owns a
+ * "symmetric" buffer (two gradient slots of `count_max` floats + `world` flag words) that its peers map through CUDA
+ * IPC.  ctvq_backward writes grad_E straight into the current slot; ctvq_peer_allreduce then (1) posts this rank's
+ * epoch into every peer's flag row, (2) waits until all peers' epochs arrived, (3) sums the `world` slots in rank
+ * order (bit-identical on every rank) scaled by `scale` into `out`.  Slots alternate by epoch parity, which makes a
+ * second barrier unnecessary.  The handle exchange is the caller's job (64-byte cudaIpcMemHandle_t per rank). */
+#define CTVQ_MAX_PEERS 8
+#define CTVQ_IPC_HANDLE_BYTES 64
+size_t ctvq_peer_buffer_bytes(size_t count_max, int world);
+int ctvq_peer_alloc(void** dev_ptr_out, size_t count_max, int world, int device);
+int ctvq_peer_free(void* dev_ptr, int device);
+int ctvq_peer_export(void* dev_ptr, void* handle64_out, int device);
+int ctvq_peer_import(const void* handle64, void** dev_ptr_out, int device);
+int ctvq_peer_close(void* dev_ptr, int device);
+/* peer_bufs: host array of `world` device pointers (entry `rank` = this rank's own buffer).  Returns the slot of
+ * epoch `epoch` through ctvq_peer_slot(). */
+float* ctvq_peer_slot(void* own_buf, size_t count_max, unsigned epoch);
+int ctvq_peer_allreduce(void* const* peer_bufs, int world, int rank, size_t count_max, size_t count, unsigned epoch,
+                        float scale, float* out, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
