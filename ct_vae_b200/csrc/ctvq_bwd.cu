@@ -180,6 +180,9 @@ int launch_backward_tiled(const BwdParams& p, cudaStream_t s) {
     const int min_tiles_per_cta = 4;
     if ((long long)grid * min_tiles_per_cta > ntiles) grid = (ntiles + min_tiles_per_cta - 1) / min_tiles_per_cta;
     if (grid < 1) grid = 1;
+    // tiny batches against a big codebook: zeroing + flushing a [C,K,d] accumulator per CTA costs more than adding the
+    // N*C*d differences straight into global memory -> let the caller fall back to the direct-atomic kernel
+    if ((double)p.N * p.C * p.d < 2.0 * (double)grid * (double)ckd) return CTVQ_E_UNSUPPORTED;
     const bool vec = (p.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.gz) & 15) == 0) &&
                      (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 15) == 0);
     cudaError_t e;
