@@ -54,6 +54,8 @@ def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], ch
             raise RuntimeError("paired inputs must share a shape")
     dev = zs[0].device
     outs = [torch.empty((b, c, h, w), dtype=torch.int64, device=dev) for _ in zs]
+    if b == 0 or h * w == 0:
+        return outs
     sp = _lib.stream_ptr(dev)
     ws = _lib.workspace(dev, sp)
     rc = _lib.lib().ctvq_argmin(_lib.ptr_array(zs), len(zs), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride,
@@ -72,9 +74,18 @@ class _Quantize(torch.autograd.Function):
         es = [e.detach() for e in codebooks]
         b, dtot, h, w, c, d, k = _shape(z, es, chan_stride)
         io_dtype = z.dtype
+        dev = z.device
+        if b == 0 or h * w == 0:
+            # empty batch: the reference returns an empty tensor and mse_loss(empty) = nan (models/vq_vae.py:47-50)
+            ctx.mark_non_differentiable()
+            empty_inds = torch.empty((b, c, h, w), dtype=torch.int64, device=dev)
+            nan = torch.full((), float("nan"), device=dev)
+            ctx.empty = True
+            return (torch.empty((b, c * d, h, w), dtype=io_dtype, device=dev), nan, empty_inds,
+                    torch.full((c,), float("nan"), device=dev))
+        ctx.empty = False
         if io_dtype == torch.bfloat16:
             z, es = _bf16_operands(z, es)
-        dev = z.device
         out = torch.empty((b, c * d, h, w), dtype=z.dtype, device=dev)
         losses = torch.empty(c + 1, dtype=torch.float32, device=dev)
         sp = _lib.stream_ptr(dev)
@@ -107,6 +118,8 @@ class _Quantize(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, g_loss, _g_inds, _g_per):
+        if ctx.empty:
+            return (None,) * len(ctx.needs_input_grad)
         z, inds, *es = ctx.saved_tensors
         beta, cs, b, dtot, h, w, c, d, k, comm = ctx.meta
         dev = z.device

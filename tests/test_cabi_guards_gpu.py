@@ -1,0 +1,105 @@
+"""Direct C-ABI calls (ctypes, raw device pointers) with GUARD BANDS around every output buffer: whatever kernel the
+dispatcher picks must not write one byte outside [B,C*d,HW] / [B,C,HW] / [C+1] / [B,Dtot,HW] / [C,K,d].
+(compute-sanitizer is closed on this GPU pool, so the tests carry their own bounds check.)  Also exercises the error
+convention of include/ctvq.h on a live device."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GUARD = 4096  # elements on each side
+SENT_F = -12345.5
+SENT_I = -77
+
+
+def _guarded(n, dtype, dev, sentinel):
+    buf = torch.full((n + 2 * GUARD,), sentinel, dtype=dtype, device=dev)
+    return buf, buf[GUARD:GUARD + n]
+
+
+def _intact(buf, n, sentinel):
+    return bool((buf[:GUARD] == sentinel).all()) and bool((buf[GUARD + n:] == sentinel).all())
+
+
+SHAPES = [
+    # B, Dtot, H, W, C, d, K, chan_stride, path
+    (6, 128, 8, 8, 4, 32, 64, 1, "auto"),     # config 2: specialised tcgen05 forward + fast backward
+    (700, 128, 8, 8, 4, 32, 64, 1, "auto"),   # ... large enough for the TMA-ring backward (N >= 37888)
+    (3, 64, 16, 16, 1, 64, 512, 1, "auto"),   # config 1: single-codebook kernel, two rounds
+    (5, 128, 8, 8, 1, 128, 64, 1, "auto"),    # config 3
+    (3, 48, 8, 4, 2, 24, 50, 24, "auto"),     # generic tcgen05 kernel (K padded to 64, HW = 32)
+    (2, 15, 3, 3, 5, 3, 7, 1, "auto"),        # ragged: SIMT + direct-atomic backward
+    (6, 128, 8, 8, 4, 32, 64, 1, "simt"),
+    (3, 64, 16, 16, 1, 64, 512, 1, "simt"),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_no_write_outside_the_output_buffers(shape):
+    from ct_vae_b200 import _lib
+    from oracle import c_oracle as CO
+    B, Dtot, H, W, C, d, K, cs, path = shape
+    HW = H * W
+    dev = torch.device("cuda:0")
+    L = _lib.lib()
+    _lib.set_path({"auto": _lib.PATH_AUTO, "simt": _lib.PATH_SIMT}[path])
+    try:
+        torch.manual_seed(3)
+        z = torch.randn(B, Dtot, H, W, device=dev)
+        books = [torch.randn(K, d, device=dev) * 0.5 for _ in range(C)]
+        ptrs = (ctypes.c_void_p * C)(*[e.data_ptr() for e in books])
+        ws = torch.zeros(L.ctvq_workspace_bytes(C, K, d), dtype=torch.uint8, device=dev)
+        sp = torch.cuda.current_stream(dev).cuda_stream
+        n_out, n_idx = B * C * d * HW, B * C * HW
+        out_b, out = _guarded(n_out, torch.float32, dev, SENT_F)
+        idx_b, idx = _guarded(n_idx, torch.int64, dev, SENT_I)
+        loss_b, loss = _guarded(C + 1, torch.float32, dev, SENT_F)
+        rc = L.ctvq_forward(z.data_ptr(), ptrs, B, Dtot, HW, C, d, K, cs, 0, 0.25, idx.data_ptr(), out.data_ptr(),
+                            loss.data_ptr(), ws.data_ptr(), ws.numel(), 0, sp)
+        assert rc == 0, L.ctvq_strerror(rc)
+        torch.cuda.synchronize()
+        assert _intact(out_b, n_out, SENT_F) and _intact(idx_b, n_idx, SENT_I) and _intact(loss_b, C + 1, SENT_F)
+        assert bool((out != SENT_F).all()) and bool((idx >= 0).all()) and bool((idx < K).all())
+        ref = CO.argmin(z.cpu(), [e.cpu() for e in books], cs)
+        assert torch.equal(idx.cpu().view(B, C, H, W), ref)
+        # backward
+        g_out = torch.randn(B, C * d, H, W, device=dev)
+        g_loss = torch.full((1,), 0.7, device=dev)
+        n_gz, n_ge = B * Dtot * HW, C * K * d
+        gz_b, gz = _guarded(n_gz, torch.float32, dev, SENT_F)
+        ge_b, ge = _guarded(n_ge, torch.float32, dev, SENT_F)
+        rc = L.ctvq_backward(z.data_ptr(), ptrs, idx.data_ptr(), g_out.data_ptr(), g_loss.data_ptr(), B, Dtot, HW, C, d,
+                             K, cs, 0, 0.25, gz.data_ptr(), ge.data_ptr(), ws.data_ptr(), ws.numel(), 0, sp)
+        assert rc == 0, L.ctvq_strerror(rc)
+        torch.cuda.synchronize()
+        assert _intact(gz_b, n_gz, SENT_F) and _intact(ge_b, n_ge, SENT_F)
+        assert bool((gz != SENT_F).all()) and bool((ge != SENT_F).all())
+        ref_gz, ref_ge = CO.backward(z.cpu(), idx.cpu().view(B, C, H, W), [e.cpu() for e in books], 0.25, g_out.cpu(),
+                                     0.7, cs)
+        assert float((gz.cpu().view_as(ref_gz) - ref_gz).abs().max() / ref_gz.abs().max()) < 1e-5
+        assert float((ge.cpu().view_as(ref_ge) - ref_ge).abs().max() / ref_ge.abs().max().clamp_min(1e-30)) < 1e-5
+    finally:
+        _lib.set_path(_lib.PATH_AUTO)
+
+
+def test_error_convention_on_device():
+    from ct_vae_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    z = torch.randn(2, 8, 2, 2, device=dev)
+    e = torch.randn(4, 8, device=dev)
+    ptrs = (ctypes.c_void_p * 1)(e.data_ptr())
+    ws = torch.zeros(L.ctvq_workspace_bytes(1, 4, 8), dtype=torch.uint8, device=dev)
+    idx = torch.empty(2, 1, 2, 2, dtype=torch.int64, device=dev)
+    out = torch.empty_like(z)
+    loss = torch.empty(2, device=dev)
+    sp = torch.cuda.current_stream(dev).cuda_stream
+    args = lambda dt, d, wsn: (z.data_ptr(), ptrs, 2, 8, 4, 1, d, 4, 1, dt, 0.25, idx.data_ptr(), out.data_ptr(),
+                               loss.data_ptr(), ws.data_ptr(), wsn, 0, sp)
+    assert L.ctvq_forward(*args(0, 8, ws.numel())) == 0
+    assert L.ctvq_forward(*args(1, 8, ws.numel())) == -2       # CTVQ_BF16 pointers: unsupported in this build
+    assert L.ctvq_forward(*args(0, 9, ws.numel())) == -1       # slice exceeds the channel count
+    assert L.ctvq_forward(*args(0, 8, 8)) == -3                # workspace too small
+    torch.cuda.synchronize()

@@ -358,3 +358,13 @@ def test_bf16_mode_is_the_fp32_contract_on_rounded_operands(env):
     assert rel_err(zb.grad.float().cpu(), gz) < 2e-2
     for q, ge in zip(m.quantizers, ges):
         assert rel_err(q.embedding.weight.grad.cpu(), ge) < TOL
+
+
+def test_empty_batch_matches_reference_semantics(env):
+    """B = 0: the reference yields an empty output and a NaN loss (mse_loss of nothing, models/vq_vae.py:47-50)."""
+    pkg, _lib, O, CO = env
+    dev = torch.device("cuda:0")
+    m = pkg.MultipleCodebookVectorQuantizer(8, 8, 2).to(dev)
+    out, loss, inds = m(torch.empty(0, 8, 3, 3, device=dev), inds=True)
+    assert out.shape == (0, 8, 3, 3) and inds.shape == (0, 2, 3, 3) and bool(torch.isnan(loss))
+    assert m.compute_inds(torch.empty(0, 8, 3, 3, device=dev)).shape == (0, 2, 3, 3)
