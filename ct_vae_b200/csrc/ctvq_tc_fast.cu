@@ -2,8 +2,11 @@
 // candidate filter, exact fp32 re-scoring, fused gather/straight-through/loss) with every inner loop unrolled
 // against compile-time D (channels per codebook), NK (padded codes per codebook) and HW, so shared-memory and
 // global addresses are immediates and the epilogue is ~4 instructions per (row, code):
-//     pass 1   a_k = fma(-2, dot_k, |e_k|^2)  and a 4-way min tree            (FFMA + FMNMX)
-//     pass 2   survivor bitmask  a_k <= min + bound                           (FSETP + predicated LOP)
+//     pass 1   s_k = z.e_k - |e_k|^2/2 comes straight out of TMEM (|e_k|^2 rides in the GEMM as one extra K-group:
+//              A = constant ones, B = -|e_k|^2/2 split into three tf32 terms); 3-input max tree       (FMNMX3)
+//     pass 2   survivor bitmask  s_k >= max - bound/2                         (FSETP + predicated LOP)
+// The fused gather / straight-through / loss runs TRANSPOSED: a lane owns 4 consecutive rows x 8 channels, so z is
+// read with 128-bit shared loads and the output leaves in 128-bit stores (indices exchanged by warp shuffles).
 // Two warpgroups (8 warps) per CTA split the codebooks by parity; 2 CTAs per SM share the 512 TMEM columns, so
 // one CTA's TMA + MMA latency hides behind the other's epilogue.
 // Replaces models/vq_vae.py:30-55 / models/mcq_vae.py:26-64,100-127 for the configs' shapes.
@@ -37,13 +40,15 @@ __device__ __forceinline__ void tmem_ld64(uint32_t addr, float (&v)[64]) {
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ float f4get(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
 struct FastParams {
     QuantParams q;
     int ntiles;
 };
 
-__device__ __forceinline__ void or_if_le(unsigned& m, float a, float lim, unsigned bit) {
-    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(a), "f"(lim), "r"(bit));
+__device__ __forceinline__ void or_if_ge(unsigned& m, float a, float lim, unsigned bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(a), "f"(lim), "r"(bit));
 }
 
 // D: channels per codebook; NK: codes per codebook padded to a multiple of 64; HWT: H*W; C: codebooks (C*NK <= 256);
@@ -63,13 +68,16 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
     constexpr uint32_t kStage = 4u * kBlk;
     constexpr uint32_t kEcb = (uint32_t)DJB * NK * 128u;
     static_assert(C * NK <= 256, "accumulator columns");
+    static_assert(NK == 64 && C * 8 <= 32 && D % 8 == 0 && HWT % 4 == 0, "shape assumptions of this kernel");
     uint8_t* a_s = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* e_s = a_s + (size_t)NSTAGE * kStage;
-    float* ee_s = reinterpret_cast<float*>(e_s + (size_t)C * kEcb);  // [C][NK]
+    uint8_t* x_s = e_s + (size_t)C * kEcb;   // [NK][32 floats], swizzled like a codebook tile: columns 8c..8c+7 = extra K-group of codebook c
+    uint8_t* ones_s = x_s + (size_t)NK * 128;  // [4 row blocks][8 channels][32 rows]: the A operand of the extra K-group
+    float* ee_s = reinterpret_cast<float*>(ones_s + 4096);  // [C][NK]
     float* emax_s = ee_s + C * NK;                                   // [C] (+pad)
     uint64_t* bars = reinterpret_cast<uint64_t*>(emax_s + ((C + 3) & ~3));  // full[NSTAGE], mma[C]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSTAGE + C);
-    const uint32_t a_base = smem_u32(a_s), e_base = smem_u32(e_s);
+    const uint32_t a_base = smem_u32(a_s), e_base = smem_u32(e_s), x_base = smem_u32(x_s), ones_base = smem_u32(ones_s);
     const uint32_t bar_full0 = smem_u32(&bars[0]), bar_m = smem_u32(&bars[NSTAGE]);
 
     if (tid == 0) {
@@ -115,7 +123,24 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
             for (int j = 0; j < D; ++j) { const float v = __ldg(row + j); a = fmaf(v, v, a); }
         }
         ee_s[i] = a;
+        // extra K-group of codebook c: -|e_k|^2/2 as three tf32-exact terms (30 mantissa bits); padded / overflowed
+        // codes get a hugely negative score so they never survive the filter
+        float t0 = -1.0e30f, t1 = 0.0f, t2 = 0.0f;
+        if (a < CUDART_INF_F) {
+            const float h = -0.5f * a;
+            t0 = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
+            const float r1 = h - t0;
+            t1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
+            t2 = __uint_as_float(__float_as_uint(r1 - t1) & 0xFFFFE000u);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+            *reinterpret_cast<float*>(x_s + e_off(k, 8 * c + jj, NK)) = jj == 0 ? t0 : (jj == 1 ? t1 : (jj == 2 ? t2 : 0.0f));
     }
+    for (int i = tid; i < NK * 32; i += kFT)  // unused columns of the extra block
+        if ((i & 31) >= 8 * C) *reinterpret_cast<float*>(x_s + e_off(i >> 5, i & 31, NK)) = 0.0f;
+    for (int i = tid; i < 1024; i += kFT)  // rows are constant, so the swizzle inside a 128-byte row is immaterial
+        reinterpret_cast<float*>(ones_s)[i] = ((i >> 5) & 7) < 3 ? 1.0f : 0.0f;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -132,6 +157,11 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
     uint32_t zsw[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ (x + wg * CS)) & 3) << 5) + ((lane & 7) << 2);
+
+    // same for the transposed gather: rows 4*(lane&7).. of the block, 16-byte granules
+    uint32_t zsw4[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) zsw4[x] = (((((lane & 7) >> 1) ^ (x + wg * CS)) & 3) << 5) + ((lane & 1) << 4);
 
     uint32_t phase_m = 0;
     float lsum[CPW];
@@ -164,6 +194,9 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                     const uint64_t bd = smem_desc(e_base + c * kEcb + (s >> 2) * NK * 128u + (s & 3) * 32u, 16u, 1024u, 2u);
                     umma_tf32(tmem_base + c * NK, ad, bd, idesc, s > 0 ? 1u : 0u);
                 }
+                // + 1 * (-|e_k|^2 / 2): the accumulator now holds the whole score z.e_k - |e_k|^2/2
+                umma_tf32(tmem_base + c * NK, smem_desc(ones_base, 1024u, 512u, 1u), smem_desc(x_base + c * 32u, 16u, 1024u, 2u),
+                          idesc, 1u);
                 umma_commit(bar_m + 8 * c);  // per-codebook completion: its epilogue starts while later codebooks multiply
             }
         }
@@ -195,62 +228,41 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                 const float* ee = ee_s + c * NK;
                 const uint8_t* zc = zblk + 2 * ci * CS * 128;  // channel j of codebook c sits at zc + j*128 + zsw[(2ciCS+j)&3]
                 const uint8_t* ecb = e_s + (size_t)c * kEcb;
-                constexpr int NCH = NK / 64;
                 float a[64];
-                // ---- pass 1: approximate distances (without |z|^2) and their minimum --------------------------------
-                float m0 = CUDART_INF_F, m1 = CUDART_INF_F, m2 = CUDART_INF_F, m3 = CUDART_INF_F;
+                // ---- pass 1: approximate scores s_k = z.e_k - |e_k|^2/2 (= -(dist_k - |z|^2)/2) and their maximum -----------
+                tmem_ld64(trow, a);
+                float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
 #pragma unroll
-                for (int chn = 0; chn < NCH; ++chn) {
-                    tmem_ld64(trow + chn * 64, a);
-#pragma unroll
-                    for (int i = 0; i < 64; i += 4) {
-                        const float4 e4 = *reinterpret_cast<const float4*>(ee + chn * 64 + i);
-                        a[i] = fmaf(-2.0f, a[i], e4.x);
-                        a[i + 1] = fmaf(-2.0f, a[i + 1], e4.y);
-                        a[i + 2] = fmaf(-2.0f, a[i + 2], e4.z);
-                        a[i + 3] = fmaf(-2.0f, a[i + 3], e4.w);
-                        m0 = fminf(m0, a[i]); m1 = fminf(m1, a[i + 1]); m2 = fminf(m2, a[i + 2]); m3 = fminf(m3, a[i + 3]);
-                    }
+                for (int i = 0; i < 64; i += 4) {
+                    m0 = fmaxf(m0, a[i]); m1 = fmaxf(m1, a[i + 1]); m2 = fmaxf(m2, a[i + 2]); m3 = fmaxf(m3, a[i + 3]);
                 }
-                const float mn = fminf(fminf(m0, m1), fminf(m2, m3));
+                const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 // rigorous bound on |tf32 distance - exact-chain distance|: both operands lose at most
-                // 2^-10 relative (truncation to 10 mantissa bits) -> |dot error| <= (2^-9 + slack) |z||e|
+                // 2^-10 relative (truncation to 10 mantissa bits) -> |dot error| <= (2^-9 + slack) |z||e|; scores are
+                // distances / -2, so the window is half the distance bound
                 const float emax = emax_s[c];
                 const float zzc = zz[ci];
                 const float thr = 2.0f * (2.0f * 2.05e-3f * sqrtf(zzc) * 1.0001f * emax + 9.5367431640625e-7f * (zzc + emax * emax));
-                const float lim = mn + thr;
+                const float lim = mx - 0.5f * thr;
                 // ---- pass 2: survivors as a bitmask ------------------------------------------------------------------------
-                unsigned mask[NCH * 2];
-                int cnt = 0;
-#pragma unroll
-                for (int chn = 0; chn < NCH; ++chn) {
-                    if (NCH > 1) {
-                        tmem_ld64(trow + chn * 64, a);
-#pragma unroll
-                        for (int i = 0; i < 64; i += 4) {
-                            const float4 e4 = *reinterpret_cast<const float4*>(ee + chn * 64 + i);
-                            a[i] = fmaf(-2.0f, a[i], e4.x);
-                            a[i + 1] = fmaf(-2.0f, a[i + 1], e4.y);
-                            a[i + 2] = fmaf(-2.0f, a[i + 2], e4.z);
-                            a[i + 3] = fmaf(-2.0f, a[i + 3], e4.w);
-                        }
-                    }
+                unsigned mask[2];
+                {
                     unsigned lo = 0u, hi = 0u;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        or_if_le(lo, a[i], lim, 1u << i);
-                        or_if_le(hi, a[32 + i], lim, 1u << i);
+                        or_if_ge(lo, a[i], lim, 1u << i);
+                        or_if_ge(hi, a[32 + i], lim, 1u << i);
                     }
-                    mask[2 * chn] = lo;
-                    mask[2 * chn + 1] = hi;
-                    cnt += __popc(lo) + __popc(hi);
+                    mask[0] = lo;
+                    mask[1] = hi;
                 }
+                const int cnt = __popc(mask[0]) + __popc(mask[1]);
                 // ---- decide ---------------------------------------------------------------------------------------------------
                 int bi = 0;
-                const bool finite = (zzc < CUDART_INF_F) && (mn > -CUDART_INF_F) && (mn < CUDART_INF_F) && cnt >= 1;
+                const bool finite = (zzc < CUDART_INF_F) && (mx > -CUDART_INF_F) && (mx < CUDART_INF_F) && cnt >= 1;
                 if (finite && cnt == 1) {
 #pragma unroll
-                    for (int w = 0; w < NCH * 2; ++w)
+                    for (int w = 0; w < 2; ++w)
                         if (mask[w]) bi = w * 32 + __ffs(mask[w]) - 1;
                 } else {
                     float bv = CUDART_INF_F;
@@ -270,7 +282,7 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                         }
                     } else {
 #pragma unroll
-                        for (int w = 0; w < NCH * 2; ++w) {
+                        for (int w = 0; w < 2; ++w) {
                             unsigned mk = mask[w];
                             while (mk) {
                                 const int k = w * 32 + __ffs(mk) - 1;
@@ -296,27 +308,41 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                 p.idx[seg][((size_t)b * C + c) * HWT + hw] = (long long)bi;
                 // ---- fused gather + straight-through + loss ------------------------------------------------------------------
                 if (p.fused) {
-                    float* out = p.q + ((size_t)b * C * D + (size_t)c * D) * HWT + hw;
-                    const uint8_t* erow = ecb + bi * 128;
-                    const uint32_t kx = (uint32_t)(bi & 7) << 4;
-                    float ls0 = 0.0f, ls1 = 0.0f;
+                    // transposed: this lane owns rows 4*q8..4*q8+3 of the warp's 32-row block and channels 8*cg..8*cg+7
+                    const int q8 = lane & 7, cg = lane >> 3;
+                    float4 ea[4], eb[4];
 #pragma unroll
-                    for (int j = 0; j < D; j += 4) {
-                        const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 + ((((j & 31) >> 2) << 4) ^ kx));
-                        const float z0 = *reinterpret_cast<const float*>(zc + j * 128 + zsw[(2 * ci * CS + j) & 3]);
-                        const float z1 = *reinterpret_cast<const float*>(zc + (j + 1) * 128 + zsw[(2 * ci * CS + j + 1) & 3]);
-                        const float z2 = *reinterpret_cast<const float*>(zc + (j + 2) * 128 + zsw[(2 * ci * CS + j + 2) & 3]);
-                        const float z3 = *reinterpret_cast<const float*>(zc + (j + 3) * 128 + zsw[(2 * ci * CS + j + 3) & 3]);
-                        const float d0 = __fsub_rn(e4.x, z0), d1 = __fsub_rn(e4.y, z1);
-                        const float d2 = __fsub_rn(e4.z, z2), d3 = __fsub_rn(e4.w, z3);
-                        out[(size_t)j * HWT] = __fadd_rn(z0, d0);  // z + (q - z), models/vq_vae.py:53
-                        out[(size_t)(j + 1) * HWT] = __fadd_rn(z1, d1);
-                        out[(size_t)(j + 2) * HWT] = __fadd_rn(z2, d2);
-                        out[(size_t)(j + 3) * HWT] = __fadd_rn(z3, d3);
-                        ls0 = fmaf(d0, d0, ls0); ls1 = fmaf(d1, d1, ls1);
-                        ls0 = fmaf(d2, d2, ls0); ls1 = fmaf(d3, d3, ls1);
+                    for (int r = 0; r < 4; ++r) {
+                        const int kr = __shfl_sync(0xffffffffu, bi, 4 * q8 + r);
+                        const uint8_t* erow = ecb + kr * 128;
+                        const uint32_t kx = (uint32_t)(kr & 7) << 4;
+                        ea[r] = *reinterpret_cast<const float4*>(erow + ((uint32_t)(cg << 5) ^ kx));
+                        eb[r] = *reinterpret_cast<const float4*>(erow + (((uint32_t)(cg << 5) + 16u) ^ kx));
                     }
-                    lsum[ci] += ls0 + ls1;
+                    const long long n4 = row0 + quarter * 32 + 4 * q8;
+                    const long long b4 = n4 / HWT;
+                    float* out = p.q + ((size_t)b4 * C * D + (size_t)c * D + 8 * cg) * HWT + (int)(n4 - b4 * HWT);
+                    const uint8_t* zl = zc + cg * 1024;
+                    float ls0 = 0.0f, ls1 = 0.0f, ls2 = 0.0f, ls3 = 0.0f;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const float4 z4 = *reinterpret_cast<const float4*>(zl + jj * 128 + zsw4[(2 * ci * CS + jj) & 3]);
+                        const float q0 = jj < 4 ? f4get(ea[0], jj) : f4get(eb[0], jj - 4);
+                        const float q1 = jj < 4 ? f4get(ea[1], jj) : f4get(eb[1], jj - 4);
+                        const float q2 = jj < 4 ? f4get(ea[2], jj) : f4get(eb[2], jj - 4);
+                        const float q3 = jj < 4 ? f4get(ea[3], jj) : f4get(eb[3], jj - 4);
+                        const float d0 = __fsub_rn(q0, z4.x), d1 = __fsub_rn(q1, z4.y);
+                        const float d2 = __fsub_rn(q2, z4.z), d3 = __fsub_rn(q3, z4.w);
+                        float4 o;
+                        o.x = __fadd_rn(z4.x, d0);  // z + (q - z), models/vq_vae.py:53
+                        o.y = __fadd_rn(z4.y, d1);
+                        o.z = __fadd_rn(z4.z, d2);
+                        o.w = __fadd_rn(z4.w, d3);
+                        *reinterpret_cast<float4*>(out + (size_t)jj * HWT) = o;
+                        ls0 = fmaf(d0, d0, ls0); ls1 = fmaf(d1, d1, ls1);
+                        ls2 = fmaf(d2, d2, ls2); ls3 = fmaf(d3, d3, ls3);
+                    }
+                    lsum[ci] += (ls0 + ls1) + (ls2 + ls3);
                 }
             }
         }
@@ -370,7 +396,7 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
     constexpr int DJB = (D + 31) / 32;
     Maps maps;
     if (make_maps(p0, maps, (C - 1) * CS + D) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;  // rows USED..USEDP-1 of the slab stay unwritten and unread
-    constexpr size_t smem = (size_t)NSTAGE * 4 * USEDP * 128 + (size_t)C * DJB * NK * 128 +
+    constexpr size_t smem = (size_t)NSTAGE * 4 * USEDP * 128 + (size_t)C * DJB * NK * 128 + (size_t)NK * 128 + 4096 +
                             sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (NSTAGE + C) * 8 + 16 + 1024;
     static_assert(smem <= 113 * 1024, "two CTAs per SM");
     auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, C, CS, NSTAGE>;
@@ -389,6 +415,7 @@ int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
     if (p.HW % 32 != 0 || p.K > 64) return CTVQ_E_UNSUPPORTED;
     for (int sg = 0; sg < p.n_seg; ++sg)
         if (reinterpret_cast<uintptr_t>(p.z[sg]) & 15) return CTVQ_E_UNSUPPORTED;
+    if (p.fused && (reinterpret_cast<uintptr_t>(p.q) & 15)) return CTVQ_E_UNSUPPORTED;  // 128-bit output stores
     if (!encode_fn()) return CTVQ_E_UNSUPPORTED;
     // configs/mcq_vae.yaml: C=4 codebooks x d=32 on overlapping slices of [B,128,8,8]
     if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) return launch_fast<32, 64, 64, 4, 1, 3>(p, s);
