@@ -5,8 +5,8 @@
 //     pass 1   s_k = z.e_k - |e_k|^2/2 comes straight out of TMEM (|e_k|^2 rides in the GEMM as one extra K-group:
 //              A = constant ones, B = -|e_k|^2/2 split into three tf32 terms); 3-input max tree       (FMNMX3)
 //     pass 2   survivor bitmask  s_k >= max - bound/2                         (FSETP + predicated LOP)
-// The fused gather / straight-through / loss runs TRANSPOSED: a lane owns 4 consecutive rows x 8 channels, so z is
-// read with 128-bit shared loads and the output leaves in 128-bit stores (indices exchanged by warp shuffles).
+// Shared-memory bandwidth is the limiter (ncu: 73 % of the L1/shared pipe), so each thread reads its row from shared
+// memory exactly once per tile into registers; |z|^2, the exact re-scoring and the gather/straight-through run from them.
 // Two warpgroups (8 warps) per CTA split the codebooks by parity; 2 CTAs per SM share the 512 TMEM columns, so
 // one CTA's TMA + MMA latency hides behind the other's epilogue.
 // Replaces models/vq_vae.py:30-55 / models/mcq_vae.py:26-64,100-127 for the configs' shapes.
@@ -16,7 +16,6 @@ namespace ctvq {
 using namespace tc;
 namespace {
 
-constexpr int kFT = 256;  // threads: 2 warpgroups x 4 warps (warp & 3 selects the TMEM lane quarter)
 
 __device__ __forceinline__ void tmem_ld64(uint32_t addr, float (&v)[64]) {
     uint32_t r[64];
@@ -40,8 +39,6 @@ __device__ __forceinline__ void tmem_ld64(uint32_t addr, float (&v)[64]) {
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float f4get(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
-
 struct FastParams {
     QuantParams q;
     int ntiles;
@@ -55,13 +52,17 @@ __device__ __forceinline__ void or_if_ge(unsigned& m, float a, float lim, unsign
 // CS: channel stride between codebook slices (1 = the reference's overlapping slices); NSTAGE: TMA ring depth.
 // ONE shared-memory slab of USEDP = round8((C-1)*CS + D) channels per row block serves every codebook: codebook c's
 // UMMA descriptors simply start c*CS rows (128 B each) into it.
-template <int D, int NK, int HWT, int C, int CS, int NSTAGE>
-__global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams P, const __grid_constant__ Maps maps) {
+// NWG: warpgroups per CTA (4 warps each; warp & 3 selects the TMEM lane quarter); warpgroup g owns codebooks g, g+NWG, ...
+template <int D, int NK, int HWT, int C, int CS, int NSTAGE, int NWG>
+__global__ void __launch_bounds__(128 * NWG, 2) vq_fwd_tc_fast_kernel(const FastParams P, const __grid_constant__ Maps maps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const QuantParams& p = P.q;
     const int K = p.K;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quarter = warp & 3, wg = warp >> 2;
-    constexpr int CPW = (C + 1) / 2;               // codebooks per warpgroup (split by parity)
+    constexpr int kFT = 128 * NWG;
+    constexpr int CPW = (C + NWG - 1) / NWG;       // codebooks per warpgroup
+    constexpr int ZSPAN = (CPW - 1) * NWG * CS + D;  // channels one warpgroup's codebooks span
+    static_assert(C % NWG == 0, "every warpgroup owns the same number of codebooks");
     constexpr int USEDP = ((C - 1) * CS + D + 7) / 8 * 8;
     constexpr int DJB = (D + 31) / 32;
     constexpr uint32_t kBlk = (uint32_t)USEDP * 128u;   // one 32-row block of the slab
@@ -158,11 +159,6 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
 #pragma unroll
     for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ (x + wg * CS)) & 3) << 5) + ((lane & 7) << 2);
 
-    // same for the transposed gather: rows 4*(lane&7).. of the block, 16-byte granules
-    uint32_t zsw4[4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x) zsw4[x] = (((((lane & 7) >> 1) ^ (x + wg * CS)) & 3) << 5) + ((lane & 1) << 4);
-
     uint32_t phase_m = 0;
     float lsum[CPW];
 #pragma unroll
@@ -201,40 +197,41 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
             }
         }
         const uint8_t* zblk = a_s + st * kStage + quarter * kBlk + wg * CS * 128;  // this warpgroup's first slice, this row block
-        // |z|^2 of this thread's row for its codebooks while the tensor core works (exact sequential chains)
+        // this thread's row, every channel its codebooks touch, read from shared memory ONCE into registers (shared-memory
+        // bandwidth is the limiter of this kernel): |z|^2, the exact re-scoring and the gather all run from zr[]
+        float zr[ZSPAN];
         float zz[CPW];
         if (valid) {
 #pragma unroll
-            for (int ci = 0; ci < CPW; ++ci) zz[ci] = 0.0f;
+            for (int j = 0; j < ZSPAN; ++j) zr[j] = *reinterpret_cast<const float*>(zblk + j * 128 + zsw[j & 3]);
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
+            for (int ci = 0; ci < CPW; ++ci) {
+                zz[ci] = 0.0f;  // exact sequential chain (arithmetic contract)
 #pragma unroll
-                for (int ci = 0; ci < CPW; ++ci) {
-                    if (wg + 2 * ci < C) {
-                        const float v = *reinterpret_cast<const float*>(zblk + (2 * ci * CS + j) * 128 + zsw[(2 * ci * CS + j) & 3]);
-                        zz[ci] = fmaf(v, v, zz[ci]);
-                    }
-                }
+                for (int j = 0; j < D; ++j) zz[ci] = fmaf(zr[NWG * ci * CS + j], zr[NWG * ci * CS + j], zz[ci]);
             }
         }
 #pragma unroll
         for (int ci = 0; ci < CPW; ++ci) {
-            const int c = wg + 2 * ci;
+            const int c = wg + NWG * ci;
             if (c >= C) continue;
             mbar_wait_fast(bar_m + 8 * c, phase_m);
             tc_fence_after();
             if (valid) {
                 const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + c * NK;
                 const float* ee = ee_s + c * NK;
-                const uint8_t* zc = zblk + 2 * ci * CS * 128;  // channel j of codebook c sits at zc + j*128 + zsw[(2ciCS+j)&3]
                 const uint8_t* ecb = e_s + (size_t)c * kEcb;
-                float a[64];
+                float a[32];
                 // ---- pass 1: approximate scores s_k = z.e_k - |e_k|^2/2 (= -(dist_k - |z|^2)/2) and their maximum -----------
-                tmem_ld64(trow, a);
+                // (two 32-column halves, re-read from TMEM in pass 2: 32 live registers instead of 64 -> twice the warps)
                 float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
 #pragma unroll
-                for (int i = 0; i < 64; i += 4) {
-                    m0 = fmaxf(m0, a[i]); m1 = fmaxf(m1, a[i + 1]); m2 = fmaxf(m2, a[i + 2]); m3 = fmaxf(m3, a[i + 3]);
+                for (int h = 0; h < 2; ++h) {
+                    tmem_ld32(trow + 32 * h, a);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        m0 = fmaxf(m0, a[i]); m1 = fmaxf(m1, a[i + 1]); m2 = fmaxf(m2, a[i + 2]); m3 = fmaxf(m3, a[i + 3]);
+                    }
                 }
                 const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 // rigorous bound on |tf32 distance - exact-chain distance|: both operands lose at most
@@ -246,15 +243,13 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                 const float lim = mx - 0.5f * thr;
                 // ---- pass 2: survivors as a bitmask ------------------------------------------------------------------------
                 unsigned mask[2];
-                {
-                    unsigned lo = 0u, hi = 0u;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        or_if_ge(lo, a[i], lim, 1u << i);
-                        or_if_ge(hi, a[32 + i], lim, 1u << i);
-                    }
-                    mask[0] = lo;
-                    mask[1] = hi;
+                for (int h = 0; h < 2; ++h) {
+                    tmem_ld32(trow + 32 * h, a);
+                    unsigned mk = 0u;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) or_if_ge(mk, a[i], lim, 1u << i);
+                    mask[h] = mk;
                 }
                 const int cnt = __popc(mask[0]) + __popc(mask[1]);
                 // ---- decide ---------------------------------------------------------------------------------------------------
@@ -274,7 +269,7 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                             float dot = 0.0f;
 #pragma unroll
                             for (int j = 0; j < D; ++j)
-                                dot = fmaf(*reinterpret_cast<const float*>(zc + j * 128 + zsw[(2 * ci * CS + j) & 3]),
+                                dot = fmaf(zr[NWG * ci * CS + j],
                                            *reinterpret_cast<const float*>(erow + (j >> 5) * NK * 128 +
                                                                            (((((j & 31) >> 2) ^ (k & 7)) & 7) << 4) + ((j & 3) << 2)), dot);
                             const float dist = dist_f32(zzc, ee[k], dot);
@@ -294,10 +289,10 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                                 for (int j = 0; j < D; j += 4) {
                                     const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 +
                                                                                        ((((j & 31) >> 2) << 4) ^ kx));
-                                    dot = fmaf(*reinterpret_cast<const float*>(zc + j * 128 + zsw[(2 * ci * CS + j) & 3]), e4.x, dot);
-                                    dot = fmaf(*reinterpret_cast<const float*>(zc + (j + 1) * 128 + zsw[(2 * ci * CS + j + 1) & 3]), e4.y, dot);
-                                    dot = fmaf(*reinterpret_cast<const float*>(zc + (j + 2) * 128 + zsw[(2 * ci * CS + j + 2) & 3]), e4.z, dot);
-                                    dot = fmaf(*reinterpret_cast<const float*>(zc + (j + 3) * 128 + zsw[(2 * ci * CS + j + 3) & 3]), e4.w, dot);
+                                    dot = fmaf(zr[NWG * ci * CS + j], e4.x, dot);
+                                    dot = fmaf(zr[NWG * ci * CS + j + 1], e4.y, dot);
+                                    dot = fmaf(zr[NWG * ci * CS + j + 2], e4.z, dot);
+                                    dot = fmaf(zr[NWG * ci * CS + j + 3], e4.w, dot);
                                 }
                                 const float dist = dist_f32(zzc, ee[k], dot);
                                 if (dist < bv) { bv = dist; bi = k; }  // ascending k: strict '<' keeps the first minimum
@@ -308,41 +303,25 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
                 p.idx[seg][((size_t)b * C + c) * HWT + hw] = (long long)bi;
                 // ---- fused gather + straight-through + loss ------------------------------------------------------------------
                 if (p.fused) {
-                    // transposed: this lane owns rows 4*q8..4*q8+3 of the warp's 32-row block and channels 8*cg..8*cg+7
-                    const int q8 = lane & 7, cg = lane >> 3;
-                    float4 ea[4], eb[4];
+                    float* out = p.q + ((size_t)b * C * D + (size_t)c * D) * HWT + hw;  // a warp's 32 rows are contiguous: 128-byte stores
+                    const uint8_t* erow = ecb + bi * 128;
+                    const uint32_t kx = (uint32_t)(bi & 7) << 4;
+                    float ls0 = 0.0f, ls1 = 0.0f;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int kr = __shfl_sync(0xffffffffu, bi, 4 * q8 + r);
-                        const uint8_t* erow = ecb + kr * 128;
-                        const uint32_t kx = (uint32_t)(kr & 7) << 4;
-                        ea[r] = *reinterpret_cast<const float4*>(erow + ((uint32_t)(cg << 5) ^ kx));
-                        eb[r] = *reinterpret_cast<const float4*>(erow + (((uint32_t)(cg << 5) + 16u) ^ kx));
-                    }
-                    const long long n4 = row0 + quarter * 32 + 4 * q8;
-                    const long long b4 = n4 / HWT;
-                    float* out = p.q + ((size_t)b4 * C * D + (size_t)c * D + 8 * cg) * HWT + (int)(n4 - b4 * HWT);
-                    const uint8_t* zl = zc + cg * 1024;
-                    float ls0 = 0.0f, ls1 = 0.0f, ls2 = 0.0f, ls3 = 0.0f;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const float4 z4 = *reinterpret_cast<const float4*>(zl + jj * 128 + zsw4[(2 * ci * CS + jj) & 3]);
-                        const float q0 = jj < 4 ? f4get(ea[0], jj) : f4get(eb[0], jj - 4);
-                        const float q1 = jj < 4 ? f4get(ea[1], jj) : f4get(eb[1], jj - 4);
-                        const float q2 = jj < 4 ? f4get(ea[2], jj) : f4get(eb[2], jj - 4);
-                        const float q3 = jj < 4 ? f4get(ea[3], jj) : f4get(eb[3], jj - 4);
-                        const float d0 = __fsub_rn(q0, z4.x), d1 = __fsub_rn(q1, z4.y);
-                        const float d2 = __fsub_rn(q2, z4.z), d3 = __fsub_rn(q3, z4.w);
-                        float4 o;
-                        o.x = __fadd_rn(z4.x, d0);  // z + (q - z), models/vq_vae.py:53
-                        o.y = __fadd_rn(z4.y, d1);
-                        o.z = __fadd_rn(z4.z, d2);
-                        o.w = __fadd_rn(z4.w, d3);
-                        *reinterpret_cast<float4*>(out + (size_t)jj * HWT) = o;
+                    for (int j = 0; j < D; j += 4) {
+                        const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 + ((((j & 31) >> 2) << 4) ^ kx));
+                        const float z0 = zr[NWG * ci * CS + j], z1 = zr[NWG * ci * CS + j + 1];
+                        const float z2 = zr[NWG * ci * CS + j + 2], z3 = zr[NWG * ci * CS + j + 3];
+                        const float d0 = __fsub_rn(e4.x, z0), d1 = __fsub_rn(e4.y, z1);
+                        const float d2 = __fsub_rn(e4.z, z2), d3 = __fsub_rn(e4.w, z3);
+                        out[(size_t)j * HWT] = __fadd_rn(z0, d0);  // z + (q - z), models/vq_vae.py:53
+                        out[(size_t)(j + 1) * HWT] = __fadd_rn(z1, d1);
+                        out[(size_t)(j + 2) * HWT] = __fadd_rn(z2, d2);
+                        out[(size_t)(j + 3) * HWT] = __fadd_rn(z3, d3);
                         ls0 = fmaf(d0, d0, ls0); ls1 = fmaf(d1, d1, ls1);
-                        ls2 = fmaf(d2, d2, ls2); ls3 = fmaf(d3, d3, ls3);
+                        ls0 = fmaf(d2, d2, ls0); ls1 = fmaf(d3, d3, ls1);
                     }
-                    lsum[ci] += (ls0 + ls1) + (ls2 + ls3);
+                    lsum[ci] += ls0 + ls1;
                 }
             }
         }
@@ -354,7 +333,7 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
     if (p.fused) {
 #pragma unroll
         for (int ci = 0; ci < CPW; ++ci) {
-            const int c = wg + 2 * ci;
+            const int c = wg + NWG * ci;
             double v = (double)lsum[ci];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -386,7 +365,7 @@ __global__ void __launch_bounds__(kFT, 2) vq_fwd_tc_fast_kernel(const FastParams
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-template <int D, int NK, int HWT, int C, int CS, int NSTAGE>
+template <int D, int NK, int HWT, int C, int CS, int NSTAGE, int NWG>
 int launch_fast(const QuantParams& p0, cudaStream_t s) {
     FastParams P;
     P.q = p0;
@@ -399,12 +378,12 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
     constexpr size_t smem = (size_t)NSTAGE * 4 * USEDP * 128 + (size_t)C * DJB * NK * 128 + (size_t)NK * 128 + 4096 +
                             sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (NSTAGE + C) * 8 + 16 + 1024;
     static_assert(smem <= 113 * 1024, "two CTAs per SM");
-    auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, C, CS, NSTAGE>;
+    auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, C, CS, NSTAGE, NWG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int grid = 148 * 2;
     if (grid > P.ntiles) grid = P.ntiles;
-    kern<<<grid, kFT, smem, s>>>(P, maps);
+    kern<<<grid, 128 * NWG, smem, s>>>(P, maps);
     return (int)cudaGetLastError();
 }
 
@@ -415,10 +394,9 @@ int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
     if (p.HW % 32 != 0 || p.K > 64) return CTVQ_E_UNSUPPORTED;
     for (int sg = 0; sg < p.n_seg; ++sg)
         if (reinterpret_cast<uintptr_t>(p.z[sg]) & 15) return CTVQ_E_UNSUPPORTED;
-    if (p.fused && (reinterpret_cast<uintptr_t>(p.q) & 15)) return CTVQ_E_UNSUPPORTED;  // 128-bit output stores
     if (!encode_fn()) return CTVQ_E_UNSUPPORTED;
     // configs/mcq_vae.yaml: C=4 codebooks x d=32 on overlapping slices of [B,128,8,8]
-    if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) return launch_fast<32, 64, 64, 4, 1, 3>(p, s);
+    if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) return launch_fast<32, 64, 64, 4, 1, 3, 2>(p, s);
     return CTVQ_E_UNSUPPORTED;
 }
 
