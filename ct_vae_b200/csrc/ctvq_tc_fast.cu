@@ -1,43 +1,27 @@
-// Shape-specialised tcgen05 forward kernel: same algorithm as ctvq_tc.cu (tf32 distance GEMM in TMEM, rigorous
-// candidate filter, exact fp32 re-scoring, fused gather/straight-through/loss) with every inner loop unrolled
-// against compile-time D (channels per codebook), NK (padded codes per codebook) and HW, so shared-memory and
-// global addresses are immediates and the epilogue is ~4 instructions per (row, code):
+// Shape-specialised tcgen05 forward kernel for the multi-codebook quantiser (configs/mcq_vae.yaml shape).
+// Same algorithm as ctvq_tc.cu (tf32 score GEMM in TMEM, rigorous candidate filter, exact fp32 re-scoring, fused
+// gather / straight-through / loss) with every inner loop unrolled against compile-time D, NK, HW, C.
+// Replaces models/vq_vae.py:30-55 / models/mcq_vae.py:26-64,100-127.
+//
+// One persistent CTA per SM, warp-specialised, NO CTA-wide barrier inside the tile loop:
+//   producer warp (one lane)  TMA ring (cp.async.bulk.tensor.3d, NSTAGE tiles of 128 rows x 35 channels) and all
+//                             tcgen05.mma groups, issued up to two tiles ahead into a DOUBLE-BUFFERED accumulator
+//                             (2 x 256 TMEM columns = all 512);
+//   16 epilogue warps         warpgroup g owns codebook g, warp (g, q) the 32 rows of TMEM lane quarter q.
+// Hand-over is mbarrier-only: full/empty per ring slot, accumulator complete / drained per (buffer, codebook), so
+// a warp that hits an expensive row (exact re-scoring) lags by itself instead of stalling the CTA.
+//
+// Per (row, code) work in the epilogue:
 //     pass 1   s_k = z.e_k - |e_k|^2/2 comes straight out of TMEM (|e_k|^2 rides in the GEMM as one extra K-group:
 //              A = constant ones, B = -|e_k|^2/2 split into three tf32 terms); 3-input max tree       (FMNMX3)
 //     pass 2   survivor bitmask  s_k >= max - bound/2                         (FSETP + predicated LOP)
-// Shared-memory bandwidth is the limiter (ncu: 73 % of the L1/shared pipe), so each thread reads its row from shared
-// memory exactly once per tile into registers; |z|^2, the exact re-scoring and the gather/straight-through run from them.
-// Two warpgroups (8 warps) per CTA split the codebooks by parity; 2 CTAs per SM share the 512 TMEM columns, so
-// one CTA's TMA + MMA latency hides behind the other's epilogue.
-// Replaces models/vq_vae.py:30-55 / models/mcq_vae.py:26-64,100-127 for the configs' shapes.
+// Shared-memory bandwidth is the limiter (ncu: L1/shared pipe), so each thread reads its row from shared memory
+// exactly once per tile into registers; |z|^2, the exact re-scoring and the gather/straight-through run from them.
 #include "ctvq_tc_ptx.cuh"
 
 namespace ctvq {
 using namespace tc;
 namespace {
-
-
-__device__ __forceinline__ void tmem_ld64(uint32_t addr, float (&v)[64]) {
-    uint32_t r[64];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
-          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
-          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
-          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
-          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(addr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 struct FastParams {
     QuantParams q;
@@ -48,49 +32,51 @@ __device__ __forceinline__ void or_if_ge(unsigned& m, float a, float lim, unsign
     asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(a), "f"(lim), "r"(bit));
 }
 
-// D: channels per codebook; NK: codes per codebook padded to a multiple of 64; HWT: H*W; C: codebooks (C*NK <= 256);
+// D: channels per codebook; NK: codes per codebook padded to 64; HWT: H*W; C: codebooks (C*NK <= 256);
 // CS: channel stride between codebook slices (1 = the reference's overlapping slices); NSTAGE: TMA ring depth.
 // ONE shared-memory slab of USEDP = round8((C-1)*CS + D) channels per row block serves every codebook: codebook c's
 // UMMA descriptors simply start c*CS rows (128 B each) into it.
-// NWG: warpgroups per CTA (4 warps each; warp & 3 selects the TMEM lane quarter); warpgroup g owns codebooks g, g+NWG, ...
-template <int D, int NK, int HWT, int C, int CS, int NSTAGE, int NWG>
-__global__ void __launch_bounds__(128 * NWG, 2) vq_fwd_tc_fast_kernel(const FastParams P, const __grid_constant__ Maps maps) {
+template <int D, int NK, int HWT, int C, int CS, int NSTAGE>
+__global__ void __launch_bounds__(128 * C + 32, 1) vq_fwd_tc_fast_kernel(const FastParams P, const __grid_constant__ Maps maps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const QuantParams& p = P.q;
     const int K = p.K;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quarter = warp & 3, wg = warp >> 2;
-    constexpr int kFT = 128 * NWG;
-    constexpr int CPW = (C + NWG - 1) / NWG;       // codebooks per warpgroup
-    constexpr int ZSPAN = (CPW - 1) * NWG * CS + D;  // channels one warpgroup's codebooks span
-    static_assert(C % NWG == 0, "every warpgroup owns the same number of codebooks");
+    constexpr int kFT = 128 * C + 32;                  // C epilogue warpgroups + the producer warp
     constexpr int USEDP = ((C - 1) * CS + D + 7) / 8 * 8;
     constexpr int DJB = (D + 31) / 32;
-    constexpr uint32_t kBlk = (uint32_t)USEDP * 128u;   // one 32-row block of the slab
+    constexpr uint32_t kBlk = (uint32_t)USEDP * 128u;  // one 32-row block of the slab
     constexpr uint32_t kStage = 4u * kBlk;
     constexpr uint32_t kEcb = (uint32_t)DJB * NK * 128u;
-    static_assert(C * NK <= 256, "accumulator columns");
-    static_assert(NK == 64 && C * 8 <= 32 && D % 8 == 0 && HWT % 4 == 0, "shape assumptions of this kernel");
+    static_assert(C * NK <= 256, "accumulator columns (two buffers fill the 512 TMEM columns)");
+    static_assert(NK == 64 && C * 8 <= 32 && D % 8 == 0 && D % 4 == 0, "shape assumptions of this kernel");
+    static_assert(NSTAGE >= 3, "the ring runs ahead of the double-buffered accumulator");
     uint8_t* a_s = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* e_s = a_s + (size_t)NSTAGE * kStage;
-    uint8_t* x_s = e_s + (size_t)C * kEcb;   // [NK][32 floats], swizzled like a codebook tile: columns 8c..8c+7 = extra K-group of codebook c
+    uint8_t* x_s = e_s + (size_t)C * kEcb;     // [NK][32 floats], swizzled like a codebook tile: columns 8c..8c+7 = extra K-group of codebook c
     uint8_t* ones_s = x_s + (size_t)NK * 128;  // [4 row blocks][8 channels][32 rows]: the A operand of the extra K-group
     float* ee_s = reinterpret_cast<float*>(ones_s + 4096);  // [C][NK]
-    float* emax_s = ee_s + C * NK;                                   // [C] (+pad)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(emax_s + ((C + 3) & ~3));  // full[NSTAGE], mma[C]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSTAGE + C);
+    float* emax_s = ee_s + C * NK;                          // [C] (+pad)
+    // mbarriers: full[NSTAGE] (TMA landed), empty[NSTAGE] (slot drained: every epilogue warp has its rows in registers
+    // and the C MMA groups that read the slab are complete), mma[2][C] (accumulator complete), tfree[2][C] (accumulator
+    // drained by its four warps)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(emax_s + ((C + 3) & ~3));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4 * C);
     const uint32_t a_base = smem_u32(a_s), e_base = smem_u32(e_s), x_base = smem_u32(x_s), ones_base = smem_u32(ones_s);
-    const uint32_t bar_full0 = smem_u32(&bars[0]), bar_m = smem_u32(&bars[NSTAGE]);
+    const uint32_t bar_full0 = smem_u32(&bars[0]), bar_empty0 = smem_u32(&bars[NSTAGE]);
+    const uint32_t bar_m = smem_u32(&bars[2 * NSTAGE]), bar_tfree = smem_u32(&bars[2 * NSTAGE + 2 * C]);
 
     if (tid == 0) {
-        for (int i = 0; i < NSTAGE; ++i) mbar_init(bar_full0 + 8 * i, 1);
-        for (int c = 0; c < C; ++c) mbar_init(bar_m + 8 * c, 1);
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full0 + 8 * i, 1); mbar_init(bar_empty0 + 8 * i, 4 * C + C); }
+        for (int i = 0; i < 2 * C; ++i) { mbar_init(bar_m + 8 * i, 1); mbar_init(bar_tfree + 8 * i, 4); }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
     __syncthreads();  // barriers initialised before the first TMA may signal them
 
     const int niter = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    auto issue = [&](int it) {  // thread 0 only: TMA-load the tile of iteration `it` into its ring slot
+    const bool producer = (tid == 128 * C);
+    auto issue_tma = [&](int it) {  // producer only: TMA-load the tile of iteration `it` into its ring slot
         const int tile = blockIdx.x + it * gridDim.x;
         const int seg = tile / p.tiles_per_seg;
         const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
@@ -105,25 +91,29 @@ __global__ void __launch_bounds__(128 * NWG, 2) vq_fwd_tc_fast_kernel(const Fast
             tma_load_3d(a_base + st * kStage + mb * kBlk, &maps.m[seg], bar_full0 + 8 * st, (int)(nb - bb * HWT), 0, (int)bb);
         }
     };
-    if (tid == 0)
-        for (int it = 0; it < NSTAGE - 1 && it < niter; ++it) issue(it);
+    if (producer)  // the first tiles stream in while the codebooks are staged
+        for (int it = 0; it < NSTAGE && it < niter; ++it) issue_tma(it);
 
-    // ---- codebooks -> K-major SWIZZLE_128B tiles (once per persistent CTA) + |e|^2 ----------------------------
-    for (int i = tid; i < C * NK * DJB * 32; i += kFT) {
-        const int j = i % (DJB * 32), ck = i / (DJB * 32), k = ck % NK, c = ck / NK;
-        const float v = (k < K && j < D) ? __ldg(p.E[c] + (size_t)k * D + j) : 0.0f;
-        *reinterpret_cast<float*>(e_s + (size_t)c * kEcb + e_off(k, j, NK)) = v;
-    }
-    for (int i = tid; i < C * NK; i += kFT) {
-        const int k = i % NK, c = i / NK;
-        float a = CUDART_INF_F;
+    // ---- codebooks -> K-major SWIZZLE_128B tiles (once per persistent CTA) + |e|^2, one code per thread -------------
+    if (tid < C * NK) {
+        const int k = tid % NK, c = tid / NK;
+        float4 v[D / 4];
         if (k < K) {
-            a = 0.0f;
-            const float* row = p.E[c] + (size_t)k * D;
-#pragma unroll 8
-            for (int j = 0; j < D; ++j) { const float v = __ldg(row + j); a = fmaf(v, v, a); }
+            const float4* row = reinterpret_cast<const float4*>(p.E[c] + (size_t)k * D);
+#pragma unroll
+            for (int m = 0; m < D / 4; ++m) v[m] = __ldg(row + m);  // all loads in flight at once
+        } else {
+#pragma unroll
+            for (int m = 0; m < D / 4; ++m) v[m] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
-        ee_s[i] = a;
+        float a = 0.0f;  // exact sequential chain (arithmetic contract)
+#pragma unroll
+        for (int m = 0; m < D / 4; ++m) {
+            *reinterpret_cast<float4*>(e_s + (size_t)c * kEcb + (m >> 3) * NK * 128 + k * 128 + (((m & 7) ^ (k & 7)) << 4)) = v[m];
+            a = fmaf(v[m].x, v[m].x, a); a = fmaf(v[m].y, v[m].y, a); a = fmaf(v[m].z, v[m].z, a); a = fmaf(v[m].w, v[m].w, a);
+        }
+        if (k >= K) a = CUDART_INF_F;
+        ee_s[tid] = a;
         // extra K-group of codebook c: -|e_k|^2/2 as three tf32-exact terms (30 mantissa bits); padded / overflowed
         // codes get a hugely negative score so they never survive the filter
         float t0 = -1.0e30f, t1 = 0.0f, t2 = 0.0f;
@@ -154,76 +144,86 @@ __global__ void __launch_bounds__(128 * NWG, 2) vq_fwd_tc_fast_kernel(const Fast
     const uint32_t tmem_base = *tmem_slot;
     __syncthreads();
 
-    // lane-dependent part of the swizzled z address, indexed by (channel & 3) relative to this warpgroup's first slice
-    uint32_t zsw[4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ (x + wg * CS)) & 3) << 5) + ((lane & 7) << 2);
-
-    uint32_t phase_m = 0;
-    float lsum[CPW];
-#pragma unroll
-    for (int ci = 0; ci < CPW; ++ci) lsum[ci] = 0.0f;
-
-    for (int it = 0; it < niter; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int seg = tile / p.tiles_per_seg;
-        const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
-        const long long n = row0 + quarter * 32 + lane;
-        const bool valid = n < p.N;  // warp-uniform (N is a multiple of 32)
-        const long long b = n / HWT;
-        const int hw = (int)(n - b * HWT);
-        const int st = it % NSTAGE;
-        if (tid == 0) {
-            if (NSTAGE == 1) issue(it);
-            else if (it + NSTAGE - 1 < niter) issue(it + NSTAGE - 1);  // slot consumed in iteration it-1
-        }
-        mbar_wait_fast(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
-        tc_fence_after();
-        const uint32_t stage_u32 = a_base + st * kStage;
-        if (tid == 0) {
+    float lsum = 0.0f;
+    if (warp == 4 * C) {
+        // =============================== producer: TMA ring + MMA groups ===========================================
+        if (lane == 0) {
             const uint32_t idesc = instr_desc_tf32(NK);
+            int tma_next = NSTAGE < niter ? NSTAGE : niter;
+            for (int it = 0; it < niter; ++it) {
+                const int st = it % NSTAGE, buf = it & 1;
+                const uint32_t stage_u32 = a_base + st * kStage;
+                mbar_wait_fast(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
+                for (int c = 0; c < C; ++c) {
+                    // accumulator (buf, c) was last read for tile it-2
+                    if (it >= 2) mbar_wait_fast(bar_tfree + 8 * (buf * C + c), (uint32_t)((it >> 1) - 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t dcol = tmem_base + buf * 256 + c * NK;
 #pragma unroll
-                for (int s = 0; s < D / 8; ++s) {
-                    const uint64_t ad = smem_desc(stage_u32 + (uint32_t)(c * CS + 8 * s) * 128u, kBlk, 512u, 1u);
-                    const uint64_t bd = smem_desc(e_base + c * kEcb + (s >> 2) * NK * 128u + (s & 3) * 32u, 16u, 1024u, 2u);
-                    umma_tf32(tmem_base + c * NK, ad, bd, idesc, s > 0 ? 1u : 0u);
+                    for (int s = 0; s < D / 8; ++s) {
+                        const uint64_t ad = smem_desc(stage_u32 + (uint32_t)(c * CS + 8 * s) * 128u, kBlk, 512u, 1u);
+                        const uint64_t bd = smem_desc(e_base + c * kEcb + (s >> 2) * NK * 128u + (s & 3) * 32u, 16u, 1024u, 2u);
+                        umma_tf32(dcol, ad, bd, idesc, s > 0 ? 1u : 0u);
+                    }
+                    // + 1 * (-|e_k|^2 / 2): the accumulator now holds the whole score z.e_k - |e_k|^2/2
+                    umma_tf32(dcol, smem_desc(ones_base, 1024u, 512u, 1u), smem_desc(x_base + c * 32u, 16u, 1024u, 2u), idesc, 1u);
+                    umma_commit(bar_m + 8 * (buf * C + c));
+                    umma_commit(bar_empty0 + 8 * st);  // the same MMAs were the last readers of this codebook's slice of the slab
                 }
-                // + 1 * (-|e_k|^2 / 2): the accumulator now holds the whole score z.e_k - |e_k|^2/2
-                umma_tf32(tmem_base + c * NK, smem_desc(ones_base, 1024u, 512u, 1u), smem_desc(x_base + c * 32u, 16u, 1024u, 2u),
-                          idesc, 1u);
-                umma_commit(bar_m + 8 * c);  // per-codebook completion: its epilogue starts while later codebooks multiply
+                // top the ring up: slot of tile tma_next was last used by tile tma_next - NSTAGE
+                while (tma_next < niter && tma_next <= it + NSTAGE - 1) {
+                    const int prev = tma_next - NSTAGE;
+                    mbar_wait_fast(bar_empty0 + 8 * (prev % NSTAGE), (uint32_t)(prev / NSTAGE) & 1u);
+                    issue_tma(tma_next);
+                    ++tma_next;
+                }
             }
         }
-        const uint8_t* zblk = a_s + st * kStage + quarter * kBlk + wg * CS * 128;  // this warpgroup's first slice, this row block
-        // this thread's row, every channel its codebooks touch, read from shared memory ONCE into registers (shared-memory
-        // bandwidth is the limiter of this kernel): |z|^2, the exact re-scoring and the gather all run from zr[]
-        float zr[ZSPAN];
-        float zz[CPW];
-        if (valid) {
+    } else {
+        // =============================== epilogue warps: codebook c = wg, rows of lane quarter ========================
+        const int c = wg;
+        // lane-dependent part of the swizzled z address, indexed by (channel & 3) relative to this codebook's first channel
+        uint32_t zsw[4];
 #pragma unroll
-            for (int j = 0; j < ZSPAN; ++j) zr[j] = *reinterpret_cast<const float*>(zblk + j * 128 + zsw[j & 3]);
-#pragma unroll
-            for (int ci = 0; ci < CPW; ++ci) {
-                zz[ci] = 0.0f;  // exact sequential chain (arithmetic contract)
-#pragma unroll
-                for (int j = 0; j < D; ++j) zz[ci] = fmaf(zr[NWG * ci * CS + j], zr[NWG * ci * CS + j], zz[ci]);
-            }
-        }
-#pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) {
-            const int c = wg + NWG * ci;
-            if (c >= C) continue;
-            mbar_wait_fast(bar_m + 8 * c, phase_m);
-            tc_fence_after();
+        for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ (x + c * CS)) & 3) << 5) + ((lane & 7) << 2);
+        const float* ee = ee_s + c * NK;
+        const uint8_t* ecb = e_s + (size_t)c * kEcb;
+        const float emax = emax_s[c];
+
+        for (int it = 0; it < niter; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int seg = tile / p.tiles_per_seg;
+            const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
+            const long long n = row0 + quarter * 32 + lane;
+            const bool valid = n < p.N;  // warp-uniform (N is a multiple of 32)
+            const long long b = n / HWT;
+            const int hw = (int)(n - b * HWT);
+            const int st = it % NSTAGE, buf = it & 1;
+            mbar_wait_fast(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
+            // this thread's row, every channel of its codebook, read from shared memory ONCE into registers
+            const uint8_t* zblk = a_s + st * kStage + quarter * kBlk + c * CS * 128;
+            float zr[D];
             if (valid) {
-                const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + c * NK;
-                const float* ee = ee_s + c * NK;
-                const uint8_t* ecb = e_s + (size_t)c * kEcb;
+#pragma unroll
+                for (int j = 0; j < D; ++j) zr[j] = *reinterpret_cast<const float*>(zblk + j * 128 + zsw[j & 3]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty0 + 8 * st);  // this warp no longer needs the slab
+            float zzc = 0.0f;  // exact sequential chain (arithmetic contract)
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) zzc = fmaf(zr[j], zr[j], zzc);
+            }
+            mbar_wait_fast(bar_m + 8 * (buf * C + c), (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + c * NK;
+            float mx = 0.0f;
+            unsigned mask0 = 0u, mask1 = 0u;
+            if (valid) {
                 float a[32];
                 // ---- pass 1: approximate scores s_k = z.e_k - |e_k|^2/2 (= -(dist_k - |z|^2)/2) and their maximum -----------
-                // (two 32-column halves, re-read from TMEM in pass 2: 32 live registers instead of 64 -> twice the warps)
+                // (two 32-column halves, re-read from TMEM in pass 2: 32 live registers instead of 64)
                 float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -233,32 +233,34 @@ __global__ void __launch_bounds__(128 * NWG, 2) vq_fwd_tc_fast_kernel(const Fast
                         m0 = fmaxf(m0, a[i]); m1 = fmaxf(m1, a[i + 1]); m2 = fmaxf(m2, a[i + 2]); m3 = fmaxf(m3, a[i + 3]);
                     }
                 }
-                const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 // rigorous bound on |tf32 distance - exact-chain distance|: both operands lose at most
                 // 2^-10 relative (truncation to 10 mantissa bits) -> |dot error| <= (2^-9 + slack) |z||e|; scores are
                 // distances / -2, so the window is half the distance bound
-                const float emax = emax_s[c];
-                const float zzc = zz[ci];
                 const float thr = 2.0f * (2.0f * 2.05e-3f * sqrtf(zzc) * 1.0001f * emax + 9.5367431640625e-7f * (zzc + emax * emax));
                 const float lim = mx - 0.5f * thr;
-                // ---- pass 2: survivors as a bitmask ------------------------------------------------------------------------
-                unsigned mask[2];
+                // ---- pass 2: survivors as a bitmask (four independent accumulators per half) ---------------------------------
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     tmem_ld32(trow + 32 * h, a);
-                    unsigned mk = 0u;
+                    unsigned mk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) or_if_ge(mk, a[i], lim, 1u << i);
-                    mask[h] = mk;
+                    for (int i = 0; i < 32; ++i) or_if_ge(mk[i & 3], a[i], lim, 1u << i);
+                    const unsigned m = (mk[0] | mk[1]) | (mk[2] | mk[3]);
+                    if (h == 0) mask0 = m; else mask1 = m;
                 }
-                const int cnt = __popc(mask[0]) + __popc(mask[1]);
+            }
+            // the accumulator is drained: hand it back to the producer for tile it+2
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tfree + 8 * (buf * C + c));
+            if (valid) {
+                const int cnt = __popc(mask0) + __popc(mask1);
                 // ---- decide ---------------------------------------------------------------------------------------------------
                 int bi = 0;
                 const bool finite = (zzc < CUDART_INF_F) && (mx > -CUDART_INF_F) && (mx < CUDART_INF_F) && cnt >= 1;
                 if (finite && cnt == 1) {
-#pragma unroll
-                    for (int w = 0; w < 2; ++w)
-                        if (mask[w]) bi = w * 32 + __ffs(mask[w]) - 1;
+                    bi = mask0 ? __ffs(mask0) - 1 : 32 + __ffs(mask1) - 1;
                 } else {
                     float bv = CUDART_INF_F;
                     bi = 0x7fffffff;
@@ -269,34 +271,31 @@ __global__ void __launch_bounds__(128 * NWG, 2) vq_fwd_tc_fast_kernel(const Fast
                             float dot = 0.0f;
 #pragma unroll
                             for (int j = 0; j < D; ++j)
-                                dot = fmaf(zr[NWG * ci * CS + j],
-                                           *reinterpret_cast<const float*>(erow + (j >> 5) * NK * 128 +
-                                                                           (((((j & 31) >> 2) ^ (k & 7)) & 7) << 4) + ((j & 3) << 2)), dot);
+                                dot = fmaf(zr[j], *reinterpret_cast<const float*>(erow + (j >> 5) * NK * 128 +
+                                                                                   (((((j & 31) >> 2) ^ (k & 7)) & 7) << 4) + ((j & 3) << 2)), dot);
                             const float dist = dist_f32(zzc, ee[k], dot);
                             if (!(dist >= bv) && (bv == bv)) { bv = dist; bi = k; }
                         }
                     } else {
+                        // exact re-scoring of the survivors, ascending k over the whole 64-bit mask (one loop: the trip count is
+                        // the warp's largest survivor count)
+                        unsigned long long mk = ((unsigned long long)mask1 << 32) | mask0;
+                        while (mk) {
+                            const int k = __ffsll((long long)mk) - 1;
+                            mk &= mk - 1;
+                            const uint8_t* erow = ecb + k * 128;
+                            const uint32_t kx = (uint32_t)(k & 7) << 4;
+                            float dot = 0.0f;
 #pragma unroll
-                        for (int w = 0; w < 2; ++w) {
-                            unsigned mk = mask[w];
-                            while (mk) {
-                                const int k = w * 32 + __ffs(mk) - 1;
-                                mk &= mk - 1;
-                                const uint8_t* erow = ecb + k * 128;
-                                const uint32_t kx = (uint32_t)(k & 7) << 4;
-                                float dot = 0.0f;
-#pragma unroll
-                                for (int j = 0; j < D; j += 4) {
-                                    const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 +
-                                                                                       ((((j & 31) >> 2) << 4) ^ kx));
-                                    dot = fmaf(zr[NWG * ci * CS + j], e4.x, dot);
-                                    dot = fmaf(zr[NWG * ci * CS + j + 1], e4.y, dot);
-                                    dot = fmaf(zr[NWG * ci * CS + j + 2], e4.z, dot);
-                                    dot = fmaf(zr[NWG * ci * CS + j + 3], e4.w, dot);
-                                }
-                                const float dist = dist_f32(zzc, ee[k], dot);
-                                if (dist < bv) { bv = dist; bi = k; }  // ascending k: strict '<' keeps the first minimum
+                            for (int j = 0; j < D; j += 4) {
+                                const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 + ((((j & 31) >> 2) << 4) ^ kx));
+                                dot = fmaf(zr[j], e4.x, dot);
+                                dot = fmaf(zr[j + 1], e4.y, dot);
+                                dot = fmaf(zr[j + 2], e4.z, dot);
+                                dot = fmaf(zr[j + 3], e4.w, dot);
                             }
+                            const float dist = dist_f32(zzc, ee[k], dot);
+                            if (dist < bv) { bv = dist; bi = k; }  // ascending k: strict '<' keeps the first minimum
                         }
                     }
                 }
@@ -310,34 +309,27 @@ __global__ void __launch_bounds__(128 * NWG, 2) vq_fwd_tc_fast_kernel(const Fast
 #pragma unroll
                     for (int j = 0; j < D; j += 4) {
                         const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 + ((((j & 31) >> 2) << 4) ^ kx));
-                        const float z0 = zr[NWG * ci * CS + j], z1 = zr[NWG * ci * CS + j + 1];
-                        const float z2 = zr[NWG * ci * CS + j + 2], z3 = zr[NWG * ci * CS + j + 3];
-                        const float d0 = __fsub_rn(e4.x, z0), d1 = __fsub_rn(e4.y, z1);
-                        const float d2 = __fsub_rn(e4.z, z2), d3 = __fsub_rn(e4.w, z3);
-                        out[(size_t)j * HWT] = __fadd_rn(z0, d0);  // z + (q - z), models/vq_vae.py:53
-                        out[(size_t)(j + 1) * HWT] = __fadd_rn(z1, d1);
-                        out[(size_t)(j + 2) * HWT] = __fadd_rn(z2, d2);
-                        out[(size_t)(j + 3) * HWT] = __fadd_rn(z3, d3);
+                        const float d0 = __fsub_rn(e4.x, zr[j]), d1 = __fsub_rn(e4.y, zr[j + 1]);
+                        const float d2 = __fsub_rn(e4.z, zr[j + 2]), d3 = __fsub_rn(e4.w, zr[j + 3]);
+                        out[(size_t)j * HWT] = __fadd_rn(zr[j], d0);  // z + (q - z), models/vq_vae.py:53
+                        out[(size_t)(j + 1) * HWT] = __fadd_rn(zr[j + 1], d1);
+                        out[(size_t)(j + 2) * HWT] = __fadd_rn(zr[j + 2], d2);
+                        out[(size_t)(j + 3) * HWT] = __fadd_rn(zr[j + 3], d3);
                         ls0 = fmaf(d0, d0, ls0); ls1 = fmaf(d1, d1, ls1);
                         ls0 = fmaf(d2, d2, ls0); ls1 = fmaf(d3, d3, ls1);
                     }
-                    lsum[ci] += ls0 + ls1;
+                    lsum += ls0 + ls1;
                 }
             }
         }
-        phase_m ^= 1;
-        tc_fence_before();
-        __syncthreads();  // TMEM columns and this ring slot are free again
     }
     // ---- loss: warp sums -> fp64 atomics -> last CTA finalises -----------------------------------------------------
     if (p.fused) {
-#pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) {
-            const int c = wg + NWG * ci;
-            double v = (double)lsum[ci];
+        if (warp < 4 * C) {
+            double v = (double)lsum;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && c < C) atomicAdd(&p.loss_acc[c], v);
+            if (lane == 0) atomicAdd(&p.loss_acc[wg], v);
         }
         __shared__ unsigned s_last;
         __threadfence();
@@ -362,10 +354,10 @@ __global__ void __launch_bounds__(128 * NWG, 2) vq_fwd_tc_fast_kernel(const Fast
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 256);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D, int NK, int HWT, int C, int CS, int NSTAGE, int NWG>
+template <int D, int NK, int HWT, int C, int CS, int NSTAGE>
 int launch_fast(const QuantParams& p0, cudaStream_t s) {
     FastParams P;
     P.q = p0;
@@ -376,14 +368,14 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
     Maps maps;
     if (make_maps(p0, maps, (C - 1) * CS + D) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;  // rows USED..USEDP-1 of the slab stay unwritten and unread
     constexpr size_t smem = (size_t)NSTAGE * 4 * USEDP * 128 + (size_t)C * DJB * NK * 128 + (size_t)NK * 128 + 4096 +
-                            sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (NSTAGE + C) * 8 + 16 + 1024;
-    static_assert(smem <= 113 * 1024, "two CTAs per SM");
-    auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, C, CS, NSTAGE, NWG>;
+                            sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (2 * NSTAGE + 4 * C) * 8 + 16 + 1024;
+    static_assert(smem <= 227 * 1024, "one CTA per SM");
+    auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, C, CS, NSTAGE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int grid = 148 * 2;
+    int grid = 148;
     if (grid > P.ntiles) grid = P.ntiles;
-    kern<<<grid, 128 * NWG, smem, s>>>(P, maps);
+    kern<<<grid, 128 * C + 32, smem, s>>>(P, maps);
     return (int)cudaGetLastError();
 }
 
@@ -394,9 +386,11 @@ int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
     if (p.HW % 32 != 0 || p.K > 64) return CTVQ_E_UNSUPPORTED;
     for (int sg = 0; sg < p.n_seg; ++sg)
         if (reinterpret_cast<uintptr_t>(p.z[sg]) & 15) return CTVQ_E_UNSUPPORTED;
+    for (int c = 0; c < p.C; ++c)
+        if (reinterpret_cast<uintptr_t>(p.E[c]) & 15) return CTVQ_E_UNSUPPORTED;  // 128-bit codebook loads
     if (!encode_fn()) return CTVQ_E_UNSUPPORTED;
     // configs/mcq_vae.yaml: C=4 codebooks x d=32 on overlapping slices of [B,128,8,8]
-    if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) return launch_fast<32, 64, 64, 4, 1, 3, 2>(p, s);
+    if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) return launch_fast<32, 64, 64, 4, 1, 6>(p, s);
     return CTVQ_E_UNSUPPORTED;
 }
 
