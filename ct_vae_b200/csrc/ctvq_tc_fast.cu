@@ -4,9 +4,11 @@
 // Replaces models/vq_vae.py:30-55 / models/mcq_vae.py:26-64,100-127.
 //
 // One persistent CTA per SM, warp-specialised, NO CTA-wide barrier inside the tile loop:
-//   producer warp (one lane)  TMA ring (cp.async.bulk.tensor.3d, NSTAGE tiles of 128 rows x 35 channels) and all
-//                             tcgen05.mma groups, issued up to two tiles ahead into a DOUBLE-BUFFERED accumulator
-//                             (2 x 256 TMEM columns = all 512);
+//   producer warp (one lane)  TMA ring (cp.async.bulk.tensor.3d, NSTAGE tiles of 128 rows x 35 channels) and the
+//                             tcgen05.mma group of each tile, issued up to two tiles ahead into a DOUBLE-BUFFERED
+//                             accumulator (2 x 256 TMEM columns = all 512).  ALL C codebooks are ONE GEMM: the B operand
+//                             is a [C*64 codes x 48] matrix holding codebook c at K-columns c*CS..c*CS+D-1 (zeros
+//                             elsewhere), so the slab and the codebooks cross the shared-memory pipe once per tile;
 //   16 epilogue warps         warpgroup g owns codebook g, warp (g, q) the 32 rows of TMEM lane quarter q.
 // Hand-over is mbarrier-only: full/empty per ring slot, accumulator complete / drained per (buffer, codebook), so
 // a warp that hits an expensive row (exact re-scoring) lags by itself instead of stalling the CTA.
@@ -22,6 +24,12 @@
 namespace ctvq {
 using namespace tc;
 namespace {
+
+__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT, 2 ulp: inside the 1.0001 slack of the bound
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 struct FastParams {
     QuantParams q;
@@ -48,27 +56,33 @@ __global__ void __launch_bounds__(128 * C + 32, 1) vq_fwd_tc_fast_kernel(const F
     constexpr uint32_t kBlk = (uint32_t)USEDP * 128u;  // one 32-row block of the slab
     constexpr uint32_t kStage = 4u * kBlk;
     constexpr uint32_t kEcb = (uint32_t)DJB * NK * 128u;
+    constexpr uint32_t kBblk = (uint32_t)C * NK * 128u;  // one K-block (32 K-columns) of the merged B operand
+    static_assert(USEDP + 8 <= 64 && USEDP >= 32 && DJB == 1, "merged B operand: two K-blocks");
     static_assert(C * NK <= 256, "accumulator columns (two buffers fill the 512 TMEM columns)");
     static_assert(NK == 64 && C * 8 <= 32 && D % 8 == 0 && D % 4 == 0, "shape assumptions of this kernel");
     static_assert(NSTAGE >= 3, "the ring runs ahead of the double-buffered accumulator");
     uint8_t* a_s = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* e_s = a_s + (size_t)NSTAGE * kStage;
-    uint8_t* x_s = e_s + (size_t)C * kEcb;     // [NK][32 floats], swizzled like a codebook tile: columns 8c..8c+7 = extra K-group of codebook c
-    uint8_t* ones_s = x_s + (size_t)NK * 128;  // [4 row blocks][8 channels][32 rows]: the A operand of the extra K-group
+    // merged B operand of the score GEMM: [2 K-blocks][C*NK rows][32 floats], K-major SWIZZLE_128B.  Row 64c+k holds
+    // E_c[k][j] at K-column c*CS+j, and -|e|^2/2 (three tf32 terms) at K-columns USEDP..USEDP+2 (the extra K-group,
+    // whose A operand is the constant-ones block); everything else is zero.  e_s above is the plain per-codebook copy
+    // the epilogue gathers from.
+    uint8_t* b_s = e_s + (size_t)C * kEcb;
+    uint8_t* ones_s = b_s + (size_t)2 * kBblk;  // [4 row blocks][8 channels][32 rows]: the A operand of the extra K-group
     float* ee_s = reinterpret_cast<float*>(ones_s + 4096);  // [C][NK]
     float* emax_s = ee_s + C * NK;                          // [C] (+pad)
     // mbarriers: full[NSTAGE] (TMA landed), empty[NSTAGE] (slot drained: every epilogue warp has its rows in registers
-    // and the C MMA groups that read the slab are complete), mma[2][C] (accumulator complete), tfree[2][C] (accumulator
-    // drained by its four warps)
+    // and the MMA group that read the slab is complete), mma[2] (accumulator buffer complete), tfree[2] (accumulator
+    // buffer drained by all 4*C epilogue warps)
     uint64_t* bars = reinterpret_cast<uint64_t*>(emax_s + ((C + 3) & ~3));
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4 * C);
-    const uint32_t a_base = smem_u32(a_s), e_base = smem_u32(e_s), x_base = smem_u32(x_s), ones_base = smem_u32(ones_s);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+    const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s), ones_base = smem_u32(ones_s);
     const uint32_t bar_full0 = smem_u32(&bars[0]), bar_empty0 = smem_u32(&bars[NSTAGE]);
-    const uint32_t bar_m = smem_u32(&bars[2 * NSTAGE]), bar_tfree = smem_u32(&bars[2 * NSTAGE + 2 * C]);
+    const uint32_t bar_m = smem_u32(&bars[2 * NSTAGE]), bar_tfree = smem_u32(&bars[2 * NSTAGE + 2]);
 
     if (tid == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full0 + 8 * i, 1); mbar_init(bar_empty0 + 8 * i, 4 * C + C); }
-        for (int i = 0; i < 2 * C; ++i) { mbar_init(bar_m + 8 * i, 1); mbar_init(bar_tfree + 8 * i, 4); }
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full0 + 8 * i, 1); mbar_init(bar_empty0 + 8 * i, 4 * C + 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_m + 8 * i, 1); mbar_init(bar_tfree + 8 * i, 4 * C); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -114,8 +128,29 @@ __global__ void __launch_bounds__(128 * C + 32, 1) vq_fwd_tc_fast_kernel(const F
         }
         if (k >= K) a = CUDART_INF_F;
         ee_s[tid] = a;
-        // extra K-group of codebook c: -|e_k|^2/2 as three tf32-exact terms (30 mantissa bits); padded / overflowed
-        // codes get a hugely negative score so they never survive the filter
+    }
+    // zero the merged B operand, the slab channels no TMA box ever writes (they meet zero B columns, but 0 * garbage
+    // could be NaN) and build the ones block
+    for (int i = tid; i < (int)(2 * kBblk / 16); i += kFT) reinterpret_cast<float4*>(b_s)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    constexpr int USED = (C - 1) * CS + D;
+    for (int i = tid; i < NSTAGE * 4 * (USEDP - USED) * 32; i += kFT) {
+        const int col = i & 31, r = (i >> 5) % (USEDP - USED), blk = (i >> 5) / (USEDP - USED);
+        reinterpret_cast<float*>(a_s + (size_t)blk * kBlk + (size_t)(USED + r) * 128)[col] = 0.0f;
+    }
+    for (int i = tid; i < 1024; i += kFT)  // rows are constant, so the swizzle inside a 128-byte row is immaterial
+        reinterpret_cast<float*>(ones_s)[i] = ((i >> 5) & 7) < 3 ? 1.0f : 0.0f;
+    __syncthreads();
+    // merged B: codebook values at their shifted K-columns ...
+    for (int i = tid; i < C * NK * D; i += kFT) {
+        const int j = i % D, k = (i / D) % NK, c = i / (D * NK);
+        const float v = *reinterpret_cast<const float*>(e_s + (size_t)c * kEcb + e_off(k, j, NK));
+        const int kk = c * CS + j, n = c * NK + k;
+        *reinterpret_cast<float*>(b_s + (size_t)(kk >> 5) * kBblk + e_off(n, kk & 31, C * NK)) = v;
+    }
+    // ... and -|e_k|^2/2 as three tf32-exact terms (30 mantissa bits) in the extra K-group; padded / overflowed codes
+    // get a hugely negative score so they never survive the filter
+    if (tid < C * NK) {
+        const float a = ee_s[tid];
         float t0 = -1.0e30f, t1 = 0.0f, t2 = 0.0f;
         if (a < CUDART_INF_F) {
             const float h = -0.5f * a;
@@ -124,14 +159,11 @@ __global__ void __launch_bounds__(128 * C + 32, 1) vq_fwd_tc_fast_kernel(const F
             t1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
             t2 = __uint_as_float(__float_as_uint(r1 - t1) & 0xFFFFE000u);
         }
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
-            *reinterpret_cast<float*>(x_s + e_off(k, 8 * c + jj, NK)) = jj == 0 ? t0 : (jj == 1 ? t1 : (jj == 2 ? t2 : 0.0f));
+        uint8_t* xb = b_s + (size_t)(USEDP >> 5) * kBblk;
+        *reinterpret_cast<float*>(xb + e_off(tid, (USEDP & 31) + 0, C * NK)) = t0;
+        *reinterpret_cast<float*>(xb + e_off(tid, (USEDP & 31) + 1, C * NK)) = t1;
+        *reinterpret_cast<float*>(xb + e_off(tid, (USEDP & 31) + 2, C * NK)) = t2;
     }
-    for (int i = tid; i < NK * 32; i += kFT)  // unused columns of the extra block
-        if ((i & 31) >= 8 * C) *reinterpret_cast<float*>(x_s + e_off(i >> 5, i & 31, NK)) = 0.0f;
-    for (int i = tid; i < 1024; i += kFT)  // rows are constant, so the swizzle inside a 128-byte row is immaterial
-        reinterpret_cast<float*>(ones_s)[i] = ((i >> 5) & 7) < 3 ? 1.0f : 0.0f;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -148,29 +180,27 @@ __global__ void __launch_bounds__(128 * C + 32, 1) vq_fwd_tc_fast_kernel(const F
     if (warp == 4 * C) {
         // =============================== producer: TMA ring + MMA groups ===========================================
         if (lane == 0) {
-            const uint32_t idesc = instr_desc_tf32(NK);
+            const uint32_t idesc = instr_desc_tf32(C * NK);
             int tma_next = NSTAGE < niter ? NSTAGE : niter;
             for (int it = 0; it < niter; ++it) {
                 const int st = it % NSTAGE, buf = it & 1;
                 const uint32_t stage_u32 = a_base + st * kStage;
                 mbar_wait_fast(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
+                // accumulator buffer `buf` was last read for tile it-2
+                if (it >= 2) mbar_wait_fast(bar_tfree + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * 256;
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    // accumulator (buf, c) was last read for tile it-2
-                    if (it >= 2) mbar_wait_fast(bar_tfree + 8 * (buf * C + c), (uint32_t)((it >> 1) - 1) & 1u);
-                    tc_fence_after();
-                    const uint32_t dcol = tmem_base + buf * 256 + c * NK;
-#pragma unroll
-                    for (int s = 0; s < D / 8; ++s) {
-                        const uint64_t ad = smem_desc(stage_u32 + (uint32_t)(c * CS + 8 * s) * 128u, kBlk, 512u, 1u);
-                        const uint64_t bd = smem_desc(e_base + c * kEcb + (s >> 2) * NK * 128u + (s & 3) * 32u, 16u, 1024u, 2u);
-                        umma_tf32(dcol, ad, bd, idesc, s > 0 ? 1u : 0u);
-                    }
-                    // + 1 * (-|e_k|^2 / 2): the accumulator now holds the whole score z.e_k - |e_k|^2/2
-                    umma_tf32(dcol, smem_desc(ones_base, 1024u, 512u, 1u), smem_desc(x_base + c * 32u, 16u, 1024u, 2u), idesc, 1u);
-                    umma_commit(bar_m + 8 * (buf * C + c));
-                    umma_commit(bar_empty0 + 8 * st);  // the same MMAs were the last readers of this codebook's slice of the slab
+                for (int s = 0; s < USEDP / 8; ++s) {  // one GEMM for all codebooks: [128 rows x USEDP] x [USEDP x C*NK]
+                    const uint64_t ad = smem_desc(stage_u32 + (uint32_t)(8 * s) * 128u, kBlk, 512u, 1u);
+                    const uint64_t bd = smem_desc(b_base + (s >> 2) * kBblk + (s & 3) * 32u, 16u, 1024u, 2u);
+                    umma_tf32(dcol, ad, bd, idesc, s > 0 ? 1u : 0u);
                 }
+                // + 1 * (-|e_k|^2 / 2): the accumulator now holds the whole score z.e_k - |e_k|^2/2
+                umma_tf32(dcol, smem_desc(ones_base, 1024u, 512u, 1u),
+                          smem_desc(b_base + ((USEDP / 8) >> 2) * kBblk + ((USEDP / 8) & 3) * 32u, 16u, 1024u, 2u), idesc, 1u);
+                umma_commit(bar_m + 8 * buf);
+                umma_commit(bar_empty0 + 8 * st);  // the same MMAs were the last readers of the slab
                 // top the ring up: slot of tile tma_next was last used by tile tma_next - NSTAGE
                 while (tma_next < niter && tma_next <= it + NSTAGE - 1) {
                     const int prev = tma_next - NSTAGE;
@@ -215,7 +245,7 @@ __global__ void __launch_bounds__(128 * C + 32, 1) vq_fwd_tc_fast_kernel(const F
 #pragma unroll
                 for (int j = 0; j < D; ++j) zzc = fmaf(zr[j], zr[j], zzc);
             }
-            mbar_wait_fast(bar_m + 8 * (buf * C + c), (uint32_t)(it >> 1) & 1u);
+            mbar_wait_fast(bar_m + 8 * buf, (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + c * NK;
             float mx = 0.0f;
@@ -237,7 +267,7 @@ __global__ void __launch_bounds__(128 * C + 32, 1) vq_fwd_tc_fast_kernel(const F
                 // rigorous bound on |tf32 distance - exact-chain distance|: both operands lose at most
                 // 2^-10 relative (truncation to 10 mantissa bits) -> |dot error| <= (2^-9 + slack) |z||e|; scores are
                 // distances / -2, so the window is half the distance bound
-                const float thr = 2.0f * (2.0f * 2.05e-3f * sqrtf(zzc) * 1.0001f * emax + 9.5367431640625e-7f * (zzc + emax * emax));
+                const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx(zzc) * 1.0001f * emax + 9.5367431640625e-7f * (zzc + emax * emax));
                 const float lim = mx - 0.5f * thr;
                 // ---- pass 2: survivors as a bitmask (four independent accumulators per half) ---------------------------------
 #pragma unroll
@@ -253,7 +283,7 @@ __global__ void __launch_bounds__(128 * C + 32, 1) vq_fwd_tc_fast_kernel(const F
             // the accumulator is drained: hand it back to the producer for tile it+2
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tfree + 8 * (buf * C + c));
+            if (lane == 0) mbar_arrive(bar_tfree + 8 * buf);
             if (valid) {
                 const int cnt = __popc(mask0) + __popc(mask1);
                 // ---- decide ---------------------------------------------------------------------------------------------------
@@ -367,8 +397,8 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
     constexpr int DJB = (D + 31) / 32;
     Maps maps;
     if (make_maps(p0, maps, (C - 1) * CS + D) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;  // rows USED..USEDP-1 of the slab stay unwritten and unread
-    constexpr size_t smem = (size_t)NSTAGE * 4 * USEDP * 128 + (size_t)C * DJB * NK * 128 + (size_t)NK * 128 + 4096 +
-                            sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (2 * NSTAGE + 4 * C) * 8 + 16 + 1024;
+    constexpr size_t smem = (size_t)NSTAGE * 4 * USEDP * 128 + (size_t)C * DJB * NK * 128 + (size_t)2 * C * NK * 128 + 4096 +
+                            sizeof(float) * ((size_t)C * NK + ((C + 3) & ~3)) + (2 * NSTAGE + 4) * 8 + 16 + 1024;
     static_assert(smem <= 227 * 1024, "one CTA per SM");
     auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, C, CS, NSTAGE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -390,7 +420,7 @@ int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
         if (reinterpret_cast<uintptr_t>(p.E[c]) & 15) return CTVQ_E_UNSUPPORTED;  // 128-bit codebook loads
     if (!encode_fn()) return CTVQ_E_UNSUPPORTED;
     // configs/mcq_vae.yaml: C=4 codebooks x d=32 on overlapping slices of [B,128,8,8]
-    if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) return launch_fast<32, 64, 64, 4, 1, 6>(p, s);
+    if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) return launch_fast<32, 64, 64, 4, 1, 5>(p, s);
     return CTVQ_E_UNSUPPORTED;
 }
 
