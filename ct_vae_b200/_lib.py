@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libctvq.so")
 _lib = None
 _lock = threading.Lock()
 
-PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
+PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC_STREAM = 0, 1, 2, 3
 F32, BF16 = 0, 1
 
 _vp, _i, _i64, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float
@@ -78,13 +78,14 @@ def require_cuda(*tensors):
 _workspaces = {}
 
 
-def workspace(device: torch.device, stream_ptr: int) -> torch.Tensor:
-    """Zero-initialised per-(device, stream) scratch the kernels keep self-cleaning."""
+def workspace(device: torch.device, stream_ptr: int, c: int = 0, k: int = 0, d: int = 0) -> torch.Tensor:
+    """Zero-initialised per-(device, stream) scratch the kernels keep self-cleaning; grown (never shrunk) to what
+    ctvq_workspace_bytes asks for the problem at hand (the streaming single-codebook kernel keeps |e|^2 there)."""
     key = (device.index, stream_ptr)
     ws = _workspaces.get(key)
-    if ws is None:
-        n = lib().ctvq_workspace_bytes(64, 0, 0)
-        ws = torch.zeros(n, dtype=torch.uint8, device=device)
+    n = lib().ctvq_workspace_bytes(c, k, d)
+    if ws is None or ws.numel() < n:
+        ws = torch.zeros(max(n, 4096), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
 

@@ -44,6 +44,11 @@ static int fill(QuantParams& p, const void* const* codebooks, int64_t B, int Dto
         p.E[c] = static_cast<const float*>(codebooks[c]);
     }
     Workspace* ws = static_cast<Workspace*>(workspace);
+    static_assert(sizeof(Workspace) <= kScratchOffset, "workspace header");
+    if (ws_bytes > kScratchOffset && !(reinterpret_cast<uintptr_t>(workspace) & 255)) {
+        p.scratch = static_cast<unsigned char*>(workspace) + kScratchOffset;
+        p.scratch_bytes = ws_bytes - kScratchOffset;
+    }
     p.loss_acc = ws->loss_acc;
     p.ticket = &ws->ticket;
     p.err = &ws->err;
@@ -56,6 +61,10 @@ static int fill(QuantParams& p, const void* const* codebooks, int64_t B, int Dto
 
 static int dispatch_forward(const QuantParams& p, cudaStream_t s) {
     const int want = g_path.load();
+    if (want == CTVQ_PATH_TC_STREAM) {
+        t_last_path = CTVQ_PATH_TC;
+        return launch_forward_tc_stream(p, s);
+    }
     if (want == CTVQ_PATH_TC || (want == CTVQ_PATH_AUTO && tc_supported(p))) {
         const int rc = launch_forward_tc(p, s);
         if (rc != CTVQ_E_UNSUPPORTED || want == CTVQ_PATH_TC) { t_last_path = CTVQ_PATH_TC; return rc; }
@@ -86,8 +95,10 @@ const char* ctvq_strerror(int rc) {
 }
 
 size_t ctvq_workspace_bytes(int C, int K, int d) {
-    (void)C; (void)K; (void)d;
-    return sizeof(Workspace);
+    (void)d;
+    // header (zero-initialised once, self-cleaning) + scratch of the streaming single-codebook kernel (no init needed);
+    // a caller that passes only the header still works: those shapes take the non-streaming kernels
+    return C == 1 && K > 0 ? kScratchOffset + stream_scratch_bytes(K) : kScratchOffset;
 }
 
 int ctvq_set_path(int path) { return g_path.exchange(path); }

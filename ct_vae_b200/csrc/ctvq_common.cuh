@@ -24,6 +24,8 @@ struct QuantParams {
     int tiles_per_seg;
     float beta;
     int fused;  // 0: argmin only, 1: argmin + gather + loss
+    unsigned char* scratch;  // optional per-stream scratch behind the Workspace header (256-byte aligned), may be null
+    size_t scratch_bytes;
 };
 
 struct Workspace {  // layout of the caller-provided zero-initialised buffer
@@ -77,5 +79,9 @@ int launch_forward_tc(const QuantParams& p, cudaStream_t s);  // returns CTVQ_E_
 bool tc_supported(const QuantParams& p);
 int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s);  // shape-specialised tcgen05 kernels
 int launch_forward_tc_c1(const QuantParams& p, cudaStream_t s);    // single-codebook row-split tcgen05 kernels
+int launch_forward_tc_stream(const QuantParams& p, cudaStream_t s);  // single codebook of any size streamed through a TMA ring
+bool stream_supported(const QuantParams& p);
+size_t stream_scratch_bytes(int K);  // scratch the streaming kernel needs behind the Workspace header
+constexpr size_t kScratchOffset = 1024;  // Workspace header rounded up
 
 }  // namespace ctvq

@@ -377,13 +377,15 @@ int make_maps(const QuantParams& p0, Maps& maps, int box_channels) {
 
 extern "C" void ctvq_debug_set_tc_dump(float* buf) { g_dbg = buf; }
 
-bool tc_supported(const QuantParams& p) { return make_plan(p).ok; }
+bool tc_supported(const QuantParams& p) { return stream_supported(p) || make_plan(p).ok; }
 
 int launch_forward_tc(const QuantParams& p0, cudaStream_t s) {
     if (!g_dbg) {
         int rc = launch_forward_tc_fast(p0, s);
         if (rc != CTVQ_E_UNSUPPORTED) return rc;
-        rc = launch_forward_tc_c1(p0, s);
+        rc = launch_forward_tc_c1(p0, s);  // resident-codebook kernels for the configs' own small-K shapes (measured faster there)
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
+        rc = launch_forward_tc_stream(p0, s);  // any K: the codebook streams through a TMA ring
         if (rc != CTVQ_E_UNSUPPORTED) return rc;
     }
     const Plan pl = make_plan(p0);

@@ -34,11 +34,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a barrier that never completes traps instead of hanging the GPU.
-// Hot-path wait: try_wait with a suspend-time hint sleeps in hardware until the phase completes (or ~1 ms
-// passes), so the loop body runs once or twice; 2048 expiries (~2 s) trap instead of hanging the GPU.
+// Hot-path wait: try_wait with a suspend-time hint parks the warp in hardware until the phase completes or the hint
+// expires (in practice after a few hundred cycles), so the loop body runs a handful of times; the bound is on TIME
+// (~4 s of SM clocks), not on iterations, because producer lanes of the streaming kernel legitimately wait for a whole
+// super-tile.
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+    long long t0 = 0;
 #pragma unroll 1
-    for (int it = 0; it < 2048; ++it) {
+    for (unsigned it = 0;; ++it) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred P1;\n\t"
@@ -46,8 +49,12 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
             "selp.b32 %0, 1, 0, P1;\n\t}"
             : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
         if (ok) return;
+        if ((it & 1023u) == 1023u) {
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 8000000000LL) __trap();
+        }
     }
-    __trap();
 }
 // Control-lane wait: tight spin (no sleep hint) so a single producer / MMA lane reacts within a few cycles of the
 // phase flip; ~2 s of polling traps instead of hanging the GPU.

@@ -57,7 +57,7 @@ def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], ch
     if b == 0 or h * w == 0:
         return outs
     sp = _lib.stream_ptr(dev)
-    ws = _lib.workspace(dev, sp)
+    ws = _lib.workspace(dev, sp, c, k, d)
     rc = _lib.lib().ctvq_argmin(_lib.ptr_array(zs), len(zs), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride,
                                 _lib.F32, _lib.ptr_array(outs), ws.data_ptr(), ws.numel(), dev.index, sp)
     _lib.check(rc, "ctvq_argmin")
@@ -89,7 +89,7 @@ class _Quantize(torch.autograd.Function):
         out = torch.empty((b, c * d, h, w), dtype=z.dtype, device=dev)
         losses = torch.empty(c + 1, dtype=torch.float32, device=dev)
         sp = _lib.stream_ptr(dev)
-        ws = _lib.workspace(dev, sp)
+        ws = _lib.workspace(dev, sp, c, k, d)
         L = _lib.lib()
         if given_inds is None:
             inds = torch.empty((b, c, h, w), dtype=torch.int64, device=dev)
@@ -136,7 +136,7 @@ class _Quantize(torch.autograd.Function):
         else:
             ge = torch.empty((c, k, d), dtype=torch.float32, device=dev)
         sp = _lib.stream_ptr(dev)
-        ws = _lib.workspace(dev, sp)
+        ws = _lib.workspace(dev, sp, c, k, d)
         rc = _lib.lib().ctvq_backward(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), go_ptr, g_loss.data_ptr(), b,
                                       dtot, h * w, c, d, k, cs, _lib.F32, beta, gz.data_ptr(), ge.data_ptr(),
                                       ws.data_ptr(), ws.numel(), dev.index, sp)

@@ -48,6 +48,7 @@ extern "C" {
 #define CTVQ_PATH_AUTO 0
 #define CTVQ_PATH_SIMT 1          /* shared-memory-staged fp32 FFMA kernel */
 #define CTVQ_PATH_TC 2            /* tcgen05/TMEM distance GEMM + exact fp32 re-scoring */
+#define CTVQ_PATH_TC_STREAM 3     /* force the streaming single-codebook tcgen05 kernel (tests / A-B; reported as CTVQ_PATH_TC) */
 
 int ctvq_version(void);
 const char* ctvq_strerror(int rc);
