@@ -410,8 +410,8 @@ def main():
          "gbs": bb * rows_per_gpu / (bwd_ms * 1e-3) / 1e9},
     ]
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full capture
-    # of this very workload (profiles/r1_final_b16384.md); only quoted for the profiled batch size
-    ncu_traffic = {16384: (146977792 + 511628032, 717342720 + 497072128)}.get(B)
+    # of this very workload (profiles/r1_fwd_ws_b16384.md); only quoted for the profiled batch size
+    ncu_traffic = {16384: (146880768 + 510873344, 717345280 + 497457664)}.get(B)
     for i, k in enumerate(kernels):
         k["frac"] = k["gbs"] / peak
         k["traffic"] = ncu_traffic[i] if ncu_traffic else None
