@@ -419,7 +419,9 @@ int launch_backward(const BwdParams& p0, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(p.gE, 0, sizeof(float) * (size_t)p.C * p.K * p.d, s);
     if (e != cudaSuccess) return (int)e;
     {
-        int rc = launch_backward_fast(p, s);  // shape-specialised (configs' shapes)
+        int rc = launch_backward_c1(p, s);    // one full-width codebook at a batch that amortises a per-CTA accumulator
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
+        rc = launch_backward_fast(p, s);      // shape-specialised (configs' shapes)
         if (rc != CTVQ_E_UNSUPPORTED) return rc;
         rc = launch_backward_tiled(p, s);     // shared-memory accumulator, no atomics in the inner loop
         if (rc != CTVQ_E_UNSUPPORTED) return rc;

@@ -136,3 +136,31 @@ def test_non_finite_rows_follow_torch_argmin(env, path, shape):
     bad = ~torch.isfinite(z_cpu).all(dim=1) | (z_cpu.abs() > 1e19).any(dim=1)   # rows with a non-finite distance
     for c in range(C):
         assert torch.equal(got[:, c][bad], ref[:, c][bad]), "non-finite rows must follow torch.argmin"
+
+
+@pytest.mark.parametrize("cfg", [
+    # (name, B, D, H, W, K): batches large enough for the single-codebook backward kernel (ctvq_bwd_c1.cu) to be chosen
+    ("bwd_d32_k256", 1024, 32, 16, 16, 256),
+    ("bwd_d64_k512_cfg1_codebook", 1024, 64, 16, 16, 512),     # configs/vq_vae.yaml at B=1024
+    ("bwd_d128_k256_tm64", 2048, 128, 8, 8, 256),              # accumulator leaves room for 64-row tiles only
+    ("bwd_d64_k200_ragged", 515, 64, 8, 8, 200),               # last tile partial, K not a power of two
+])
+def test_single_codebook_backward_at_scale(env, cfg):
+    """grad_z and the codebook-gradient scatter-add against the C oracle at sizes where the
+    shared-atomic single-codebook kernel runs; 1e-5 relative (atomics reorder the fp32 sums)."""
+    pkg, _lib, O, CO = env
+    name, B, D, H, W, K = cfg
+    dev = torch.device("cuda:0")
+    torch.manual_seed(99)
+    m = _module(pkg, K, D, "trained", dev)
+    z_cpu = torch.randn(B, D, H, W)
+    g_out = torch.randn(B, D, H, W)
+    z = z_cpu.to(dev).requires_grad_(True)
+    out, loss, inds = m(z, inds=True)
+    (out * g_out.to(dev)).sum().add(0.7 * loss).backward()
+    torch.cuda.synchronize()
+    book = [m.embedding.weight.detach().cpu()]
+    inds_cpu = inds.cpu().reshape(B, 1, H, W)
+    gz, ge = CO.backward(z_cpu, inds_cpu, book, 0.25, g_out, 0.7)
+    assert rel_err(z.grad.cpu(), gz) < TOL
+    assert rel_err(m.embedding.weight.grad.cpu(), ge.reshape(K, D)) < TOL
