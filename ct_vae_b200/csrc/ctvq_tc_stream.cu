@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
     constexpr int DJB = D / 32;
     constexpr int NBUF = 8 / T;                      // TMEM unit slots per team
     constexpr int TCOLS = 512 / T;
-    constexpr bool ZREG = (D <= 32);                 // row kept in registers (else re-read from the resident slab)
+    constexpr bool ZREG = (D * T <= 128);            // row kept in registers when the register file allows (else re-read from the resident slab)
     constexpr uint32_t kBlkA = (uint32_t)D * 128u;   // one 32-row block: [D][128 B]
     constexpr uint32_t kASZ = (uint32_t)T * 4u * kBlkA;
     static_assert(D % 32 == 0 && (T == 1 || T == 2 || T == 4), "shape");
@@ -258,9 +258,27 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
             };
             // rigorous bound on |tf32 distance - exact-chain distance|; scores are distances / -2
             const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx_s(zz) * 1.0001f * emax + 9.5367431640625e-7f * (zz + emax * emax));
-            float run_mx = -CUDART_INF_F, run_bv = CUDART_INF_F;
-            int run_bi = 0x7fffffff;
+            // Running state.  Exact distances are only needed to COMPARE candidates, so a lone candidate stays "pending" with
+            // an upper bound of its approximate score; it is dropped unscored as soon as a later unit lifts the window above
+            // that bound (the usual fate of every provisional maximum), and exact-scored entries are dropped the same way.
+            // Rows whose final window holds a single code never compute an exact distance at all.
+            float run_mx = -CUDART_INF_F, run_bv = CUDART_INF_F, pend_ub = 0.0f, ex_ub = -CUDART_INF_F;
+            int run_bi = 0x7fffffff, pend_k = -1;
             bool bad = !(zz < CUDART_INF_F);
+            auto score = [&](int k) {  // exact fp32 distance of code k (arithmetic contract); callers go in ascending k
+                const float4* erow = reinterpret_cast<const float4*>(E + (size_t)k * D);
+                float dot = 0.0f;
+#pragma unroll(ZREG ? D / 4 : 8)
+                for (int j = 0; j < D; j += 4) {
+                    const float4 e4 = __ldg(erow + (j >> 2));
+                    dot = fmaf(zat(j), e4.x, dot);
+                    dot = fmaf(zat(j + 1), e4.y, dot);
+                    dot = fmaf(zat(j + 2), e4.z, dot);
+                    dot = fmaf(zat(j + 3), e4.w, dot);
+                }
+                const float dist = dist_f32(zz, __ldg(P.ee + k), dot);
+                if (dist < run_bv) { run_bv = dist; run_bi = k; }  // strict '<' keeps the first minimum
+            };
 #pragma unroll 1
             for (int kc = 0; kc < NU; ++kc) {
                 const long long g = (long long)s * NU + kc;
@@ -302,30 +320,31 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                 if (lane == 0) mbar_arrive(bar_tfree + 8 * (team * NBUF + slot));  // slot free for unit g + NBUF
                 if (valid) {
                     if (!(mxu > -CUDART_INF_F) || !(mxu < CUDART_INF_F)) bad = true;
-                    unsigned long long mk = ((unsigned long long)mask1 << 32) | mask0;
-                    if (NU == 1 && !bad && __popcll(mk) == 1) {
-                        run_bi = __ffsll((long long)mk) - 1;  // single unit, single survivor: no exact score needed
-                    } else if (!bad) {
-                        while (mk) {
-                            const int k = kc * 64 + __ffsll((long long)mk) - 1;
-                            mk &= mk - 1;
-                            if (k < K) {
-                                const float4* erow = reinterpret_cast<const float4*>(E + (size_t)k * D);
-                                float dot = 0.0f;
-#pragma unroll 8
-                                for (int j = 0; j < D; j += 4) {
-                                    const float4 e4 = __ldg(erow + (j >> 2));
-                                    dot = fmaf(zat(j), e4.x, dot);
-                                    dot = fmaf(zat(j + 1), e4.y, dot);
-                                    dot = fmaf(zat(j + 2), e4.z, dot);
-                                    dot = fmaf(zat(j + 3), e4.w, dot);
-                                }
-                                const float dist = dist_f32(zz, __ldg(P.ee + k), dot);
-                                if (dist < run_bv) { run_bv = dist; run_bi = k; }  // ascending k: strict '<' keeps the first minimum
+                    if (!bad) {
+                        unsigned long long mk = ((unsigned long long)mask1 << 32) | mask0;
+                        const float lim = run_mx - 0.5f * thr;
+                        // everything older whose approximate score cannot reach the window any more is out
+                        if (pend_k >= 0 && pend_ub < lim) pend_k = -1;
+                        if (run_bi != 0x7fffffff && ex_ub < lim) { run_bi = 0x7fffffff; run_bv = CUDART_INF_F; }
+                        const int cnt = __popcll(mk);
+                        if (cnt == 1 && pend_k < 0 && run_bi == 0x7fffffff && kc * 64 + __ffsll((long long)mk) - 1 < K) {
+                            pend_k = kc * 64 + __ffsll((long long)mk) - 1;  // nothing to compare it with: stays unscored
+                            pend_ub = run_mx;
+                        } else if (cnt >= 1) {
+                            if (pend_k >= 0) { score(pend_k); pend_k = -1; }  // older unit = smaller k: ascending order holds
+                            while (mk) {
+                                const int k = kc * 64 + __ffsll((long long)mk) - 1;
+                                mk &= mk - 1;
+                                if (k < K) score(k);
                             }
+                            ex_ub = run_mx;
                         }
                     }
                 }
+            }
+            if (valid && !bad && pend_k >= 0) {
+                if (run_bi == 0x7fffffff) run_bi = pend_k;  // the only code in the final window
+                else score(pend_k);                       // later unit than every scored entry: ascending order holds
             }
             if (valid) {
                 if (bad || run_bi == 0x7fffffff) {
@@ -346,7 +365,7 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                     float* out = p.q + (size_t)b * D * HW + hw;  // a warp's 32 rows are contiguous: 128-byte stores
                     const float4* erow = reinterpret_cast<const float4*>(E + (size_t)bi * D);
                     float ls0 = 0.0f, ls1 = 0.0f;
-#pragma unroll 8
+#pragma unroll(ZREG ? D / 4 : 8)
                     for (int j = 0; j < D; j += 4) {
                         const float4 e4 = __ldg(erow + (j >> 2));
                         const float z0 = zat(j), z1 = zat(j + 1), z2 = zat(j + 2), z3 = zat(j + 3);
@@ -465,7 +484,7 @@ bool stream_supported(const QuantParams& p) {
 int launch_forward_tc_stream(const QuantParams& p, cudaStream_t s) {
     if (!stream_supported(p)) return CTVQ_E_UNSUPPORTED;
     if (p.d == 32) return launch_stream<32, 4, 2>(p, s);
-    if (p.d == 64) return launch_stream<64, 4, 1>(p, s);
+    if (p.d == 64) return launch_stream<64, 2, 2>(p, s);  // rows in registers + double-buffered slabs: 0.46 ms vs 0.63 ms (T=4) at K=512, 1 M rows
     if (p.d == 128) return launch_stream<128, 2, 1>(p, s);
     if (p.d == 256) return launch_stream<256, 1, 1>(p, s);
     return CTVQ_E_UNSUPPORTED;

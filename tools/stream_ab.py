@@ -32,8 +32,14 @@ for N, D, K, HW, kind in pts:
         with torch.no_grad():
             return m(z, inds=True)
 
+    if os.environ.get("CTVQ_FORCE_STREAM"):
+        _lib.set_path(_lib.PATH_TC_STREAM)
+    if os.environ.get("CTVQ_ONLY_D") and int(os.environ["CTVQ_ONLY_D"]) != D:
+        continue
     t = time_ms(fwd, 10, flush if N * D * 4 < 200e6 else None)
     nb = max(1, 2048 // HW)
+    if os.environ.get("CTVQ_FORCE_STREAM"):
+        _lib.set_path(_lib.PATH_TC_STREAM)
     with torch.no_grad():
         _, _, inds = m(z[:nb], inds=True)
     ref = CO.argmin(z[:nb].cpu(), [m.embedding.weight.detach().cpu()])
