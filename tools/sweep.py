@@ -83,7 +83,7 @@ def point(N, D, K, C, HW, kind, dev, flush):
     ok = bool(torch.equal(inds.cpu().reshape(ref.shape), ref))
     return dict(N=N, D=D, K=K, C=C, HW=HW, codebook=kind, path=path, fwd_ms=t_f, fwdbwd_ms=t_fb,
                 fwd_Mlat_s=N / t_f / 1e3, fwdbwd_Mlat_s=N / t_fb / 1e3, fwd_gbs=fb * N / t_f / 1e6,
-                fwd_frac=fb * N / t_f / 1e6 / PEAK, fwdbwd_gbs=(fb + bb) * N / t_fb / 1e6,
+                fwd_frac=fb * N / t_f / 1e6 / PEAK, fwd_tflops=2.0 * N * K * d * C / t_f / 1e9, fwdbwd_gbs=(fb + bb) * N / t_fb / 1e6,
                 fwdbwd_frac=(fb + bb) * N / t_fb / 1e6 / PEAK, idx_exact=ok)
 
 
@@ -103,6 +103,7 @@ def main():
         (1 << 16, 32, 256, 1, 256, "trained"), (1 << 20, 32, 256, 1, 256, "trained"), (1 << 22, 32, 256, 1, 256, "trained"),
         (1 << 20, 64, 256, 1, 256, "trained"), (1 << 20, 128, 256, 1, 256, "trained"), (1 << 18, 256, 256, 1, 256, "trained"),
         (1 << 20, 64, 1024, 1, 256, "trained"), (1 << 18, 128, 4096, 1, 256, "trained"), (1 << 16, 256, 16384, 1, 256, "trained"),
+        (1 << 20, 32, 16384, 1, 256, "trained"),
     ]
     if not args.quick:
         pts += [(1 << 24, 32, 256, 1, 256, "trained")]
@@ -142,16 +143,17 @@ def main():
     with open(args.out, "w") as f:
         f.write("# round 1 — quantiser microbenchmark sweep (BASELINE.json configs[3]) and Gaussian branch (configs[4])\n\n")
         f.write(f"One B200, fp32, CUDA-event median, HBM peak {PEAK:.0f} GB/s (MEASURED_PEAKS.json). `frac` = algorithmic bytes ÷ time ÷ peak "
-                "(HBM roofline; points with K ≥ 1024 are bound by the SIMT FFMA rate / epilogue issue, not HBM — next round). "
+                "(HBM roofline). `fwd TF/s` = 2*K*D flops per row / time: the points with K >= 1024 are TENSOR-bound (tf32 peak taken as "
+                "half the measured bf16 burst peak of 1670 TF/s, i.e. 835 TF/s) and run the streaming tcgen05 kernel. "
                 "`idx_exact` = indices equal to the C oracle on a 4096-row sample.\n\n")
-        f.write("| N | D | K | C | HW | codebook | path | fwd ms | fwd M lat/s | fwd GB/s | fwd frac | fwd+bwd ms | fwd+bwd M lat/s | fwd+bwd GB/s | fwd+bwd frac | idx_exact |\n")
-        f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        f.write("| N | D | K | C | HW | codebook | path | fwd ms | fwd M lat/s | fwd GB/s | fwd frac | fwd TF/s | fwd+bwd ms | fwd+bwd M lat/s | fwd+bwd GB/s | fwd+bwd frac | idx_exact |\n")
+        f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         for r in rows:
             if "error" in r:
                 f.write(f"| {r['N']} | {r['D']} | {r['K']} | {r['C']} | {r['HW']} | {r['codebook']} | error: {r['error']} |\n")
                 continue
             f.write(f"| {r['N']} | {r['D']} | {r['K']} | {r['C']} | {r['HW']} | {r['codebook']} | {r['path']} | {r['fwd_ms']:.4f} | "
-                    f"{r['fwd_Mlat_s']:.1f} | {r['fwd_gbs']:.0f} | {r['fwd_frac']:.3f} | {r['fwdbwd_ms']:.4f} | {r['fwdbwd_Mlat_s']:.1f} | "
+                    f"{r['fwd_Mlat_s']:.1f} | {r['fwd_gbs']:.0f} | {r['fwd_frac']:.3f} | {r['fwd_tflops']:.0f} | {r['fwdbwd_ms']:.4f} | {r['fwdbwd_Mlat_s']:.1f} | "
                     f"{r['fwdbwd_gbs']:.0f} | {r['fwdbwd_frac']:.3f} | {r['idx_exact']} |\n")
         f.write("\n## reparameterise + KL (16 B/element forward: mu, logvar, eps in, z out; backward +24 B)\n\n")
         f.write("| B | L | fwd ms | fwd GB/s | fwd frac | fwd+bwd ms | fwd+bwd GB/s | fwd+bwd frac |\n|---|---|---|---|---|---|---|---|\n")
