@@ -53,7 +53,9 @@ extern "C" {
 int ctvq_version(void);
 const char* ctvq_strerror(int rc);
 
-/* Bytes of zero-initialised device workspace one stream needs for a problem with C codebooks. */
+/* Bytes of zero-initialised device workspace one stream needs: a 1 KB self-cleaning header, plus -- for C == 1 -- the
+ * scratch of the streaming single-codebook kernel (|e_k|^2 and its tf32-split GEMM blocks: K*4 + ceil(K/256)*8 KB,
+ * rewritten each call).  Passing only ctvq_workspace_bytes(0,0,0) is valid: such calls take the other kernels. */
 size_t ctvq_workspace_bytes(int C, int K, int d);
 
 /* Force a kernel path for subsequent calls on this thread's library handle (tests/bench); AUTO picks
