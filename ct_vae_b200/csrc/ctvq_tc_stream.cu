@@ -258,12 +258,15 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
             };
             // rigorous bound on |tf32 distance - exact-chain distance|; scores are distances / -2
             const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx_s(zz) * 1.0001f * emax + 9.5367431640625e-7f * (zz + emax * emax));
-            // Running state.  Exact distances are only needed to COMPARE candidates, so a lone candidate stays "pending" with
-            // an upper bound of its approximate score; it is dropped unscored as soon as a later unit lifts the window above
-            // that bound (the usual fate of every provisional maximum), and exact-scored entries are dropped the same way.
-            // Rows whose final window holds a single code never compute an exact distance at all.
-            float run_mx = -CUDART_INF_F, run_bv = CUDART_INF_F, pend_ub = 0.0f, ex_ub = -CUDART_INF_F;
-            int run_bi = 0x7fffffff, pend_k = -1;
+            // Running state.  Exact distances are only needed to COMPARE candidates, and an L2 round trip per unit would stall
+            // the few warps an SM has, so survivors are QUEUED (three register slots: code + an upper bound of its
+            // approximate score = the running maximum when it was queued, hence non-decreasing along the queue).  A later
+            // unit that lifts the window above the oldest bounds drops them unscored -- the usual fate of every provisional
+            // maximum -- and what is left at the end of the row is scored in one go, two chains interleaved; a row whose
+            // final window holds a single code never computes an exact distance.  Queue overflow settles it exactly.
+            float run_mx = -CUDART_INF_F, run_bv = CUDART_INF_F, ex_ub = -CUDART_INF_F;
+            float qu0 = 0.0f, qu1 = 0.0f, qu2 = 0.0f;
+            int run_bi = 0x7fffffff, qk0 = -1, qk1 = -1, qk2 = -1, qn = 0;
             bool bad = !(zz < CUDART_INF_F);
             auto score = [&](int k) {  // exact fp32 distance of code k (arithmetic contract); callers go in ascending k
                 const float4* erow = reinterpret_cast<const float4*>(E + (size_t)k * D);
@@ -278,6 +281,27 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                 }
                 const float dist = dist_f32(zz, __ldg(P.ee + k), dot);
                 if (dist < run_bv) { run_bv = dist; run_bi = k; }  // strict '<' keeps the first minimum
+            };
+            auto score2 = [&](int ka, int kb) {  // two codes (ka < kb, kb may be -1): both rows in flight, chains interleaved
+                const float4* ra = reinterpret_cast<const float4*>(E + (size_t)ka * D);
+                const float4* rb = reinterpret_cast<const float4*>(E + (size_t)(kb >= 0 ? kb : ka) * D);
+                float da = 0.0f, db = 0.0f;
+#pragma unroll(ZREG ? D / 4 : 8)
+                for (int j = 0; j < D; j += 4) {
+                    const float4 a4 = __ldg(ra + (j >> 2));
+                    const float4 b4 = __ldg(rb + (j >> 2));
+                    const float z0 = zat(j), z1 = zat(j + 1), z2 = zat(j + 2), z3 = zat(j + 3);
+                    da = fmaf(z0, a4.x, da); db = fmaf(z0, b4.x, db);
+                    da = fmaf(z1, a4.y, da); db = fmaf(z1, b4.y, db);
+                    da = fmaf(z2, a4.z, da); db = fmaf(z2, b4.z, db);
+                    da = fmaf(z3, a4.w, da); db = fmaf(z3, b4.w, db);
+                }
+                const float dista = dist_f32(zz, __ldg(P.ee + ka), da);
+                if (dista < run_bv) { run_bv = dista; run_bi = ka; }
+                if (kb >= 0) {
+                    const float distb = dist_f32(zz, __ldg(P.ee + kb), db);
+                    if (distb < run_bv) { run_bv = distb; run_bi = kb; }
+                }
             };
 #pragma unroll 1
             for (int kc = 0; kc < NU; ++kc) {
@@ -323,28 +347,36 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                     if (!bad) {
                         unsigned long long mk = ((unsigned long long)mask1 << 32) | mask0;
                         const float lim = run_mx - 0.5f * thr;
-                        // everything older whose approximate score cannot reach the window any more is out
-                        if (pend_k >= 0 && pend_ub < lim) pend_k = -1;
+                        // everything older whose approximate score cannot reach the window any more is out: a PREFIX of the queue
+                        const int drop = ((qn > 0 && qu0 < lim) ? 1 : 0) + ((qn > 1 && qu1 < lim) ? 1 : 0) + ((qn > 2 && qu2 < lim) ? 1 : 0);
+                        if (drop == 1) { qk0 = qk1; qu0 = qu1; qk1 = qk2; qu1 = qu2; }
+                        else if (drop == 2) { qk0 = qk2; qu0 = qu2; }
+                        qn -= drop;
                         if (run_bi != 0x7fffffff && ex_ub < lim) { run_bi = 0x7fffffff; run_bv = CUDART_INF_F; }
-                        const int cnt = __popcll(mk);
-                        if (cnt == 1 && pend_k < 0 && run_bi == 0x7fffffff && kc * 64 + __ffsll((long long)mk) - 1 < K) {
-                            pend_k = kc * 64 + __ffsll((long long)mk) - 1;  // nothing to compare it with: stays unscored
-                            pend_ub = run_mx;
-                        } else if (cnt >= 1) {
-                            if (pend_k >= 0) { score(pend_k); pend_k = -1; }  // older unit = smaller k: ascending order holds
-                            while (mk) {
-                                const int k = kc * 64 + __ffsll((long long)mk) - 1;
-                                mk &= mk - 1;
-                                if (k < K) score(k);
+                        while (mk) {
+                            const int k = kc * 64 + __ffsll((long long)mk) - 1;
+                            mk &= mk - 1;
+                            if (k >= K) continue;
+                            if (qn < 3) {
+                                if (qn == 0) { qk0 = k; qu0 = run_mx; } else if (qn == 1) { qk1 = k; qu1 = run_mx; } else { qk2 = k; qu2 = run_mx; }
+                                ++qn;
+                            } else {  // overflow: settle the queue exactly (ascending k), then this code
+                                score2(qk0, qk1);
+                                score2(qk2, k);
+                                qn = 0;
+                                ex_ub = run_mx;
                             }
-                            ex_ub = run_mx;
                         }
                     }
                 }
             }
-            if (valid && !bad && pend_k >= 0) {
-                if (run_bi == 0x7fffffff) run_bi = pend_k;  // the only code in the final window
-                else score(pend_k);                       // later unit than every scored entry: ascending order holds
+            if (valid && !bad) {
+                if (qn == 1 && run_bi == 0x7fffffff) {
+                    run_bi = qk0;  // the only code in the final window: no exact distance needed
+                } else if (qn >= 1) {  // queued codes are younger (larger k) than every scored entry: ascending order holds
+                    score2(qk0, qn >= 2 ? qk1 : -1);
+                    if (qn == 3) score(qk2);
+                }
             }
             if (valid) {
                 if (bad || run_bi == 0x7fffffff) {
