@@ -5,6 +5,6 @@ Product: libctvq.so — hand-written CUDA kernels behind the C ABI in include/ct
 """
 from .modules import (MultipleCodebookVectorQuantizer, VectorQuantizer, VectorQuantizerMS,  # noqa: F401
                       attach_grad_comm)
-from . import functional, gaussian, patch  # noqa: F401
+from . import ct_codec, functional, gaussian, patch  # noqa: F401
 
 __version__ = "0.1.0"

@@ -27,6 +27,10 @@ _SIGNATURES = {
     "ctvq_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _i, _vp]),
     "ctvq_reparam_kld_fwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "ctvq_reparam_kld_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp]),
+    "ctvq_onehot_from_inds": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_inds_from_onehot": (_i, [_vp, _i64, _i64, _i, _vp, _i, _vp]),
+    "ctvq_latent_ce_fwd": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_latent_ce_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _vp, _i, _vp]),
     "ctvq_nccl_load": (_i, [ctypes.c_char_p]),
     "ctvq_nccl_unique_id": (_i, [_vp]),
     "ctvq_nccl_comm_init": (_i, [ctypes.POINTER(_vp), _i, _i, _vp, _i]),

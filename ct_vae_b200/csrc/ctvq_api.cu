@@ -214,6 +214,45 @@ int ctvq_reparam_kld_bwd(const float* mu, const float* logvar, const float* eps,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CT-mode codec: index <-> one-hot, one-hot cross-entropy (models/ct_mcq_vae.py:472-496, 306-311)
+// ---------------------------------------------------------------------------------------------------
+int ctvq_onehot_from_inds(const int64_t* idx, int64_t B, int64_t S, int K, float* onehot_out, void* workspace,
+                          size_t ws_bytes, int device, void* stream) {
+    if (!idx || !onehot_out || !workspace || B <= 0 || S <= 0 || K <= 0) return CTVQ_E_BADARG;
+    if (ws_bytes < sizeof(Workspace)) return CTVQ_E_WORKSPACE;
+    DeviceGuard g(device);
+    if (g.err != cudaSuccess) return (int)g.err;
+    return launch_onehot(reinterpret_cast<const long long*>(idx), B, S, K, onehot_out, &static_cast<Workspace*>(workspace)->err,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int ctvq_inds_from_onehot(const float* scores, int64_t B, int64_t S, int K, int64_t* idx_out, int device, void* stream) {
+    if (!scores || !idx_out || B <= 0 || S <= 0 || K <= 0) return CTVQ_E_BADARG;
+    DeviceGuard g(device);
+    if (g.err != cudaSuccess) return (int)g.err;
+    return launch_class_argmax(scores, B, S, K, reinterpret_cast<long long*>(idx_out), static_cast<cudaStream_t>(stream));
+}
+
+int ctvq_latent_ce_fwd(const float* latent, const float* latent_y, int64_t B, int64_t S, int K, int64_t* target_out,
+                       float* rowsum_out, float* loss_out, void* workspace, size_t ws_bytes, int device, void* stream) {
+    if (!latent || !latent_y || !target_out || !rowsum_out || !loss_out || !workspace || B <= 0 || S <= 0 || K <= 0) return CTVQ_E_BADARG;
+    if (ws_bytes < sizeof(Workspace)) return CTVQ_E_WORKSPACE;
+    DeviceGuard g(device);
+    if (g.err != cudaSuccess) return (int)g.err;
+    return launch_latent_ce_fwd(latent, latent_y, B, S, K, reinterpret_cast<long long*>(target_out), rowsum_out, loss_out,
+                                static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+int ctvq_latent_ce_bwd(const float* latent, const int64_t* target, const float* rowsum, const float* g_loss, int64_t B,
+                       int64_t S, int K, float* g_latent_out, int device, void* stream) {
+    if (!latent || !target || !rowsum || !g_loss || !g_latent_out || B <= 0 || S <= 0 || K <= 0) return CTVQ_E_BADARG;
+    DeviceGuard g(device);
+    if (g.err != cudaSuccess) return (int)g.err;
+    return launch_latent_ce_bwd(latent, reinterpret_cast<const long long*>(target), rowsum, g_loss, B, S, K, g_latent_out,
+                                static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------
 // NCCL (dlopen: the library has no link-time dependency on libnccl, so it loads on hosts without it)
 // ---------------------------------------------------------------------------------------------------
 namespace {

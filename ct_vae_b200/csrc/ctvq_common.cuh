@@ -76,6 +76,12 @@ int launch_reparam_fwd(const float* mu, const float* lv, const float* eps, long 
                        Workspace* ws, cudaStream_t s);
 int launch_reparam_bwd(const float* mu, const float* lv, const float* eps, const float* g_z, const float* g_kld,
                        long long B, int L, float* g_mu, float* g_lv, cudaStream_t s);
+int launch_onehot(const long long* idx, long long B, long long S, int K, float* out, unsigned int* err, cudaStream_t s);
+int launch_class_argmax(const float* x, long long B, long long S, int K, long long* idx, cudaStream_t s);
+int launch_latent_ce_fwd(const float* x, const float* y, long long B, long long S, int K, long long* tgt, float* rowsum,
+                         float* loss, Workspace* ws, cudaStream_t s);
+int launch_latent_ce_bwd(const float* x, const long long* tgt, const float* rowsum, const float* g_loss, long long B,
+                         long long S, int K, float* gx, cudaStream_t s);
 int launch_forward_tc(const QuantParams& p, cudaStream_t s);  // returns CTVQ_E_UNSUPPORTED when shape not covered
 bool tc_supported(const QuantParams& p);
 int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s);  // shape-specialised tcgen05 kernels

@@ -112,6 +112,27 @@ int ctvq_reparam_kld_bwd(const float* mu, const float* logvar, const float* eps,
                          const float* g_kld, int64_t B, int L, float* g_mu_out, float* g_logvar_out,
                          int device, void* stream);
 
+/* CT-mode codec -- the converters either side of the quantiser in CausalTransition mode.
+ * One-hots are fp32 [B, K, S] contiguous with S = C*H*W (the reference's [B, N, K*H, W] tensor after its permute,
+ * models/ct_mcq_vae.py:481-482), indices int64 [B, S] (= [B, C, H, W]).
+ *   ctvq_onehot_from_inds  replaces CTMCQVAE.ct_preprocess  (models/ct_mcq_vae.py:472-483): F.one_hot + view + permute.
+ *                          An index outside [0, K) leaves its row all-zero and is flagged in the workspace (the
+ *                          reference raises from F.one_hot).
+ *   ctvq_inds_from_onehot  replaces CTMCQVAE.ct_postprocess (models/ct_mcq_vae.py:485-496): permute + reshape +
+ *                          torch.argmax over the class dimension (first maximum wins, the first NaN wins).
+ *   ctvq_latent_ce_fwd/bwd replace CausalTransition.latent_CrossEntropy_loss (models/ct_mcq_vae.py:306-311):
+ *                          loss = mean_rows( log(sum_k x'_k) - log(x'_t) ), x' = max(latent, 1e-4), t = argmax_k latent_y;
+ *                          fwd also returns the targets [B,S] and the row sums [B,S] the backward re-uses;
+ *                          bwd: g_latent = g_loss/(B*S) * [latent >= 1e-4] * (1/sum' - [k==t]/x'_t); latent_y gets no
+ *                          gradient (it is detached at models/ct_mcq_vae.py:300). */
+int ctvq_onehot_from_inds(const int64_t* idx, int64_t B, int64_t S, int K, float* onehot_out, void* workspace,
+                          size_t ws_bytes, int device, void* stream);
+int ctvq_inds_from_onehot(const float* scores, int64_t B, int64_t S, int K, int64_t* idx_out, int device, void* stream);
+int ctvq_latent_ce_fwd(const float* latent, const float* latent_y, int64_t B, int64_t S, int K, int64_t* target_out,
+                       float* rowsum_out, float* loss_out, void* workspace, size_t ws_bytes, int device, void* stream);
+int ctvq_latent_ce_bwd(const float* latent, const int64_t* target, const float* rowsum, const float* g_loss, int64_t B,
+                       int64_t S, int K, float* g_latent_out, int device, void* stream);
+
 /* Codebook-gradient all-reduce — the one collective of the path (replaces the share of Lightning's DDP
  * bucket all-reduce that carries vq_layer.*.embedding.weight.grad, run.py:99).  NCCL is dlopen()ed from
  * `libnccl_path` (the torch-bundled libnccl.so.2); communicators are created from a 128-byte unique id

@@ -201,3 +201,27 @@ def reparam_kld_backward(mu: Tensor, logvar: Tensor, eps: Tensor, g_z: Tensor, g
     g_mu = g_z + g_kld * mu / b
     g_lv = g_z * eps * 0.5 * torch.exp(0.5 * logvar) + g_kld * (-0.5 / b) * (1 - logvar.exp())
     return g_mu, g_lv
+
+
+# ---- CT-mode codec: restated on the same ATen CPU operators as the reference ------------------
+def ct_preprocess(x: Tensor, latents_shape: Sequence[int], num_embeddings: int, codebooks: int) -> Tensor:
+    """models/ct_mcq_vae.py:472-483: one-hot of the code indices, [B,K,H,W] -> [B,N,K*H,W]."""
+    oh = torch.nn.functional.one_hot(x, num_classes=num_embeddings).to(dtype=torch.float32)
+    oh = oh.view((latents_shape[0], codebooks * latents_shape[2], latents_shape[3], num_embeddings))
+    return oh.permute(0, 3, 1, 2)
+
+
+def ct_postprocess(x: Tensor, latents_shape: Sequence[int], num_embeddings: int, codebooks: int) -> Tensor:
+    """models/ct_mcq_vae.py:485-496: argmax over the class dimension, [B,N,K*H,W] -> [B,K,H,W]."""
+    y = x.permute(0, 2, 3, 1)
+    y = y.reshape((latents_shape[0], codebooks, latents_shape[2], latents_shape[3], num_embeddings))
+    return torch.argmax(y, dim=-1)
+
+
+def latent_cross_entropy_loss(latent: Tensor, latent_y: Tensor) -> Tensor:
+    """models/ct_mcq_vae.py:306-311: cross-entropy of log(clamp(latent, 1e-4)) against argmax(latent_y)."""
+    a = latent.permute(0, 2, 3, 1).reshape((-1, latent.size(1)))
+    a = a.clamp(min=1e-4).log()
+    t = latent_y.permute(0, 2, 3, 1).reshape((-1, latent_y.size(1)))
+    t = torch.argmax(t, dim=-1)
+    return torch.nn.functional.cross_entropy(a, t)

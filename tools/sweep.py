@@ -16,7 +16,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ct_vae_b200 as pkg  # noqa: E402
-from ct_vae_b200 import _lib, gaussian  # noqa: E402
+from ct_vae_b200 import _lib, ct_codec, gaussian  # noqa: E402
 from oracle import c_oracle as CO  # noqa: E402
 
 PEAK = 6549.1
@@ -140,6 +140,31 @@ def main():
                  fwdbwd_gbs=(16 + 24) * B * L / tfb / 1e6, fwdbwd_frac=(16 + 24) * B * L / tfb / 1e6 / PEAK)
         g.append(r)
         print(json.dumps(r), flush=True)
+    # CT-mode codec: one-hot <-> index converters and the one-hot cross-entropy
+    ct = []
+    for B, C, H, W, N in ((16, 1, 8, 8, 64), (16384, 4, 8, 8, 64)):
+        shape = [B, 128, H, W]
+        inds = torch.randint(0, N, (B, C, H, W), device=dev)
+        onehot = ct_codec.ct_preprocess(inds, shape, N, C)
+        lat = (torch.rand(B, N, C * H, W, device=dev) * 0.1).requires_grad_(True)
+        lat_y = torch.rand(B, N, C * H, W, device=dev)
+        one = torch.ones((), device=dev)
+        nrows = B * C * H * W
+        fl = flush if nrows * N * 4 < 200e6 else None
+
+        def ce_fb():
+            loss = ct_codec.latent_cross_entropy_loss(lat, lat_y)
+            torch.autograd.backward([loss], [one])
+            lat.grad = None
+
+        t_pre = time_ms(lambda: ct_codec.ct_preprocess(inds, shape, N, C), 20, fl)
+        t_post = time_ms(lambda: ct_codec.ct_postprocess(onehot, shape, N, C), 20, fl)
+        t_ce = time_ms(ce_fb, 20, fl)
+        r = dict(B=B, C=C, HW=H * W, N=N, rows=nrows, pre_ms=t_pre, pre_gbs=nrows * (4 * N + 8) / t_pre / 1e6,
+                 post_ms=t_post, post_gbs=nrows * (4 * N + 8) / t_post / 1e6, ce_ms=t_ce,
+                 ce_gbs=nrows * (8 * N + 12 + 4 * N + 12 + 4 * N) / t_ce / 1e6)
+        ct.append(r)
+        print(json.dumps(r), flush=True)
     with open(args.out, "w") as f:
         f.write("# round 1 — quantiser microbenchmark sweep (BASELINE.json configs[3]) and Gaussian branch (configs[4])\n\n")
         f.write(f"One B200, fp32, CUDA-event median, HBM peak {PEAK:.0f} GB/s (MEASURED_PEAKS.json). `frac` = algorithmic bytes ÷ time ÷ peak "
@@ -160,6 +185,11 @@ def main():
         for r in g:
             f.write(f"| {r['B']} | {r['L']} | {r['fwd_ms']:.4f} | {r['fwd_gbs']:.0f} | {r['fwd_frac']:.3f} | {r['fwdbwd_ms']:.4f} | "
                     f"{r['fwdbwd_gbs']:.0f} | {r['fwdbwd_frac']:.3f} |\n")
+        f.write("\n## CT-mode codec (models/ct_mcq_vae.py:472-496, 306-311): one-hot [B,N,C*H,W] fp32 <-> indices, one-hot cross-entropy fwd+bwd\n\n")
+        f.write("| B | C | HW | N | rows | ct_preprocess ms | GB/s | frac | ct_postprocess ms | GB/s | frac | latent CE fwd+bwd ms | GB/s | frac |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        for r in ct:
+            f.write(f"| {r['B']} | {r['C']} | {r['HW']} | {r['N']} | {r['rows']} | {r['pre_ms']:.4f} | {r['pre_gbs']:.0f} | {r['pre_gbs'] / PEAK:.3f} | "
+                    f"{r['post_ms']:.4f} | {r['post_gbs']:.0f} | {r['post_gbs'] / PEAK:.3f} | {r['ce_ms']:.4f} | {r['ce_gbs']:.0f} | {r['ce_gbs'] / PEAK:.3f} |\n")
     print("wrote", args.out)
 
 
