@@ -109,26 +109,18 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     if (producer)  // the first tiles stream in while the codebooks are staged
         for (int it = 0; it < NSTAGE && it < niter; ++it) issue_tma(it);
 
-    // ---- codebooks -> K-major SWIZZLE_128B tiles (once per persistent CTA) + |e|^2, one code per thread -------------
+    // ---- codebooks (once per persistent CTA), one code per thread: the global loads fly while everybody zero-fills ----
+    float4 v[D / 4];
+    const int ck = tid % NK, cc = tid / NK;  // code, codebook of this thread (tid < C*NK)
     if (tid < C * NK) {
-        const int k = tid % NK, c = tid / NK;
-        float4 v[D / 4];
-        if (k < K) {
-            const float4* row = reinterpret_cast<const float4*>(p.E[c] + (size_t)k * D);
+        if (ck < K) {
+            const float4* row = reinterpret_cast<const float4*>(p.E[cc] + (size_t)ck * D);
 #pragma unroll
             for (int m = 0; m < D / 4; ++m) v[m] = __ldg(row + m);  // all loads in flight at once
         } else {
 #pragma unroll
             for (int m = 0; m < D / 4; ++m) v[m] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
-        float a = 0.0f;  // exact sequential chain (arithmetic contract)
-#pragma unroll
-        for (int m = 0; m < D / 4; ++m) {
-            *reinterpret_cast<float4*>(e_s + (size_t)c * kEcb + (m >> 3) * NK * 128 + k * 128 + (((m & 7) ^ (k & 7)) << 4)) = v[m];
-            a = fmaf(v[m].x, v[m].x, a); a = fmaf(v[m].y, v[m].y, a); a = fmaf(v[m].z, v[m].z, a); a = fmaf(v[m].w, v[m].w, a);
-        }
-        if (k >= K) a = CUDART_INF_F;
-        ee_s[tid] = a;
     }
     // zero the merged B operand, the slab channels no TMA box ever writes (they meet zero B columns, but 0 * garbage
     // could be NaN) and build the ones block
@@ -140,18 +132,28 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     }
     for (int i = tid; i < 1024; i += kFT)  // rows are constant, so the swizzle inside a 128-byte row is immaterial
         reinterpret_cast<float*>(ones_s)[i] = ((i >> 5) & 7) < 3 ? 1.0f : 0.0f;
+    if (tid < C) reinterpret_cast<unsigned*>(emax_s)[tid] = 0u;
     __syncthreads();
-    // merged B: codebook values at their shifted K-columns ...
-    for (int i = tid; i < C * NK * D; i += kFT) {
-        const int j = i % D, k = (i / D) % NK, c = i / (D * NK);
-        const float v = *reinterpret_cast<const float*>(e_s + (size_t)c * kEcb + e_off(k, j, NK));
-        const int kk = c * CS + j, n = c * NK + k;
-        *reinterpret_cast<float*>(b_s + (size_t)(kk >> 5) * kBblk + e_off(n, kk & 31, C * NK)) = v;
-    }
-    // ... and -|e_k|^2/2 as three tf32-exact terms (30 mantissa bits) in the extra K-group; padded / overflowed codes
-    // get a hugely negative score so they never survive the filter
     if (tid < C * NK) {
-        const float a = ee_s[tid];
+        // plain per-codebook copy (the epilogue gathers from it), merged B at the shifted K-columns, exact |e|^2
+        float a = 0.0f;  // exact sequential chain (arithmetic contract)
+        const int n = cc * NK + ck;
+#pragma unroll
+        for (int m = 0; m < D / 4; ++m) {
+            *reinterpret_cast<float4*>(e_s + (size_t)cc * kEcb + (m >> 3) * NK * 128 + ck * 128 + (((m & 7) ^ (ck & 7)) << 4)) = v[m];
+            const float x[4] = {v[m].x, v[m].y, v[m].z, v[m].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = cc * CS + 4 * m + u;
+                *reinterpret_cast<float*>(b_s + (size_t)(kk >> 5) * kBblk + e_off(n, kk & 31, C * NK)) = x[u];
+                a = fmaf(x[u], x[u], a);
+            }
+        }
+        if (ck >= K) a = CUDART_INF_F;
+        ee_s[tid] = a;
+        if (ck < K) atomicMax(reinterpret_cast<unsigned*>(emax_s) + cc, __float_as_uint(a));  // a >= 0: bit order = value order
+        // -|e_k|^2/2 as three tf32-exact terms (30 mantissa bits) in the extra K-group; padded / overflowed codes get a
+        // hugely negative score so they never survive the filter
         float t0 = -1.0e30f, t1 = 0.0f, t2 = 0.0f;
         if (a < CUDART_INF_F) {
             const float h = -0.5f * a;
@@ -169,11 +171,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid < C) {
-        float mx = 0.0f;
-        for (int k = 0; k < K; ++k) mx = fmaxf(mx, ee_s[tid * NK + k]);
-        emax_s[tid] = sqrtf(mx) * 1.0001f;
-    }
+    if (tid < C) emax_s[tid] = sqrtf(__uint_as_float(reinterpret_cast<unsigned*>(emax_s)[tid])) * 1.0001f;
     const uint32_t tmem_base = *tmem_slot;
     __syncthreads();
 
