@@ -284,7 +284,9 @@ def main():
         collective = args.collective
         if collective == "peer":
             try:
-                comm = PeerGradComm(CFG["C"] * CFG["K"] * (CFG["D"] // CFG["C"]), dev)
+                # overlap: the all-reduce of step i runs on a side stream underneath the forward of step i+1 (its result is
+                # only needed by the optimizer); every timed region ends with comm.wait(), so all of them are inside it
+                comm = PeerGradComm(CFG["C"] * CFG["K"] * (CFG["D"] // CFG["C"]), dev, overlap=True)
             except Exception as e:  # no CUDA IPC / peer access on this box: NCCL carries the collective instead
                 print(f"[bench] peer collective unavailable ({e!r}); using NCCL", file=sys.stderr)
                 collective = "nccl"
@@ -314,6 +316,10 @@ def main():
             p.grad = None
         return loss
 
+    def comm_wait():  # the overlapped all-reduce of the last step belongs to the timed region
+        if comm is not None and hasattr(comm, "wait"):
+            comm.wait()
+
     def sync_all():
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -332,6 +338,7 @@ def main():
             flush.zero_()
             a.record()
             step(z)
+            comm_wait()
             b.record()
         sync_all()
         ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -341,6 +348,7 @@ def main():
         e0.record()
         for _ in range(args.steps):
             step(z)
+        comm_wait()
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
@@ -380,6 +388,7 @@ def main():
         with torch.no_grad():
             dz.copy_(host_z, non_blocking=True)
         loss = step(dz)
+        comm_wait()
         host_loss.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the user reads the loss (experiment.py:96 .item())
         return float(host_loss)

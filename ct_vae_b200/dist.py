@@ -93,10 +93,18 @@ class PeerGradComm:
     (bit-identical on every rank), scaled by 1/world.  torch.distributed only carries the 64-byte IPC handles.
     Single node, world <= 8 (every GPU reaches every peer through NVSwitch)."""
 
-    def __init__(self, count_max: int, device: torch.device, group=None, average: bool = True):
+    def __init__(self, count_max: int, device: torch.device, group=None, average: bool = True, overlap: bool = False):
+        """overlap=True launches the all-reduce kernel on a private side stream (ordered after the backward kernel by an
+        event), so it runs underneath whatever the caller enqueues next -- the next forward, the encoder's backward.
+        The caller must then call ``wait()`` before it READS the reduced gradient (optimizer step); the next backward
+        waits by itself before it reuses a slot."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (it carries the IPC handles)")
         self.group, self.device = group, device
+        self.overlap = bool(overlap)
+        self._side = torch.cuda.Stream(device=device) if overlap else None
+        self._ready = torch.cuda.Event() if overlap else None   # backward kernel finished writing the slot
+        self._done = None                                        # last all-reduce finished (side stream)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         if self.world > 8:
@@ -132,18 +140,37 @@ class PeerGradComm:
             n *= int(s)
         if n > self.count_max:
             raise RuntimeError(f"codebook gradient ({n} floats) exceeds the symmetric buffer ({self.count_max})")
+        if self._done is not None:
+            # the slot about to be rewritten was last read by the peers during all-reduce (epoch - 1); our all-reduce of
+            # `epoch` completing proves every peer has finished that one
+            torch.cuda.current_stream(self.device).wait_event(self._done)
         slot = _lib.lib().ctvq_peer_slot(self._own, self.count_max, self.epoch + 1)
         return torch.as_tensor(_DeviceArray(slot, n), device=self.device).view(*shape)
 
     def allreduce_(self, grad: torch.Tensor) -> torch.Tensor:
         self.epoch += 1
         out = torch.empty(grad.shape, dtype=torch.float32, device=self.device)
+        if self.overlap:
+            main = torch.cuda.current_stream(self.device)
+            self._ready.record(main)
+            self._side.wait_event(self._ready)
+            sp = self._side.cuda_stream
+            out.record_stream(self._side)
+        else:
+            sp = _lib.stream_ptr(self.device)
         rc = _lib.lib().ctvq_peer_allreduce(self._table, self.world, self.rank, self.count_max, grad.numel(),
-                                            self.epoch, self.scale, out.data_ptr(), self.device.index,
-                                            _lib.stream_ptr(self.device))
+                                            self.epoch, self.scale, out.data_ptr(), self.device.index, sp)
         _lib.check(rc, "ctvq_peer_allreduce")
+        if self.overlap:
+            self._done = torch.cuda.Event()
+            self._done.record(self._side)
         self.launches += 1
         return out
+
+    def wait(self) -> None:
+        """Make the current stream wait for the last all-reduce (no-op without overlap)."""
+        if self._done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done)
 
     def close(self):
         L = _lib.lib()

@@ -20,7 +20,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
@@ -29,7 +29,7 @@ def _worker(rank, world, port, q):
         import ct_vae_b200 as pkg
         from ct_vae_b200.dist import PeerGradComm
         C, K, D = 4, 64, 128
-        comm = PeerGradComm(C * K * (D // C), dev)
+        comm = PeerGradComm(C * K * (D // C), dev, overlap=overlap)
         worst = 0.0
         for epoch in range(5):
             torch.manual_seed(100 * epoch + rank)
@@ -37,6 +37,7 @@ def _worker(rank, world, port, q):
             buf = comm.grad_buffer((C, K, D // C))
             buf.copy_(g)
             out = comm.allreduce_(buf)
+            comm.wait()  # overlap mode: the reduced gradient is about to be read
             parts = [torch.empty_like(g) for _ in range(world)]
             dist.all_gather(parts, g)
             exp = torch.zeros_like(g)
@@ -54,6 +55,7 @@ def _worker(rank, world, port, q):
         z = torch.randn(32, D, 8, 8, device=dev, requires_grad=True)
         out, loss = m(z)
         (out.sum() * 0.01 + loss).backward()
+        comm.wait()
         mine = torch.stack([qz.embedding.weight.grad for qz in m.quantizers])
         pkg.attach_grad_comm(m, None)
         for qz in m.quantizers:
@@ -73,11 +75,13 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_peer_allreduce_two_gpus():
+@pytest.mark.parametrize("overlap", [False, True])
+def test_peer_allreduce_two_gpus(overlap):
+    """overlap=True: the all-reduce kernel runs on a side stream (bench.py default), wait() joins it."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
