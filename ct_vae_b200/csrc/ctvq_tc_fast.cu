@@ -271,11 +271,14 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
                 // distances / -2, so the window is half the distance bound
                 const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx(zzc) * 1.0001f * emax + 9.5367431640625e-7f * (zzc + emax * emax));
                 const float lim = mx - 0.5f * thr;
-                // ---- pass 2: survivors as a bitmask (four independent accumulators per half) ---------------------------------
+                // ---- pass 2: survivors as a bitmask (four independent accumulators per half); the upper half is still in
+                // registers from pass 1, only the lower half is re-read from TMEM
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    tmem_ld32_issue(trow + 32 * h, a);
-                    tmem_ld32_wait(a);
+                for (int h = 1; h >= 0; --h) {
+                    if (h == 0) {
+                        tmem_ld32_issue(trow, a);
+                        tmem_ld32_wait(a);
+                    }
                     unsigned mk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int i = 0; i < 32; ++i) or_if_ge(mk[i & 3], __uint_as_float(a[i]), lim, 1u << i);
@@ -313,22 +316,27 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
                         // exact re-scoring of the survivors, ascending k over the whole 64-bit mask (one loop: the trip count is
                         // the warp's largest survivor count)
                         unsigned long long mk = ((unsigned long long)mask1 << 32) | mask0;
-                        while (mk) {
-                            const int k = __ffsll((long long)mk) - 1;
+                        while (mk) {  // two candidates per trip: both code rows in flight, the two FMA chains interleaved
+                            const int ka = __ffsll((long long)mk) - 1;
                             mk &= mk - 1;
-                            const uint8_t* erow = ecb + k * 128;
-                            const uint32_t kx = (uint32_t)(k & 7) << 4;
-                            float dot = 0.0f;
+                            const int kb = mk ? __ffsll((long long)mk) - 1 : ka;
+                            mk &= mk - 1;
+                            const uint8_t* ra = ecb + ka * 128;
+                            const uint8_t* rb = ecb + kb * 128;
+                            const uint32_t xa = (uint32_t)(ka & 7) << 4, xb = (uint32_t)(kb & 7) << 4;
+                            float da = 0.0f, db = 0.0f;
 #pragma unroll
                             for (int j = 0; j < D; j += 4) {
-                                const float4 e4 = *reinterpret_cast<const float4*>(erow + (j >> 5) * NK * 128 + ((((j & 31) >> 2) << 4) ^ kx));
-                                dot = fmaf(zr[j], e4.x, dot);
-                                dot = fmaf(zr[j + 1], e4.y, dot);
-                                dot = fmaf(zr[j + 2], e4.z, dot);
-                                dot = fmaf(zr[j + 3], e4.w, dot);
+                                const float4 a4 = *reinterpret_cast<const float4*>(ra + (j >> 5) * NK * 128 + ((((j & 31) >> 2) << 4) ^ xa));
+                                const float4 b4 = *reinterpret_cast<const float4*>(rb + (j >> 5) * NK * 128 + ((((j & 31) >> 2) << 4) ^ xb));
+                                da = fmaf(zr[j], a4.x, da); db = fmaf(zr[j], b4.x, db);
+                                da = fmaf(zr[j + 1], a4.y, da); db = fmaf(zr[j + 1], b4.y, db);
+                                da = fmaf(zr[j + 2], a4.z, da); db = fmaf(zr[j + 2], b4.z, db);
+                                da = fmaf(zr[j + 3], a4.w, da); db = fmaf(zr[j + 3], b4.w, db);
                             }
-                            const float dist = dist_f32(zzc, ee[k], dot);
-                            if (dist < bv) { bv = dist; bi = k; }  // ascending k: strict '<' keeps the first minimum
+                            const float dista = dist_f32(zzc, ee[ka], da), distb = dist_f32(zzc, ee[kb], db);
+                            if (dista < bv) { bv = dista; bi = ka; }  // ascending k: strict '<' keeps the first minimum
+                            if (distb < bv) { bv = distb; bi = kb; }  // (kb == ka when the mask ran out: no-op)
                         }
                     }
                 }
