@@ -34,8 +34,12 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(const PeerParams p)
     if (threadIdx.x < p.world) {
         const unsigned int* f = p.flags[p.rank] + threadIdx.x;
         const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(f) - p.epoch) < 0)
+        // back off between polls: in overlap mode this kernel shares its SMs with the next forward, whose persistent CTAs
+        // have a static share of the tiles -- a warp spinning at full rate on one scheduler slows the whole kernel
+        while ((int)(ld_acquire_sys(f) - p.epoch) < 0) {
+            __nanosleep(400);
             if (clock64() - t0 > 6000000000LL) __trap();  // ~3 s: a missing peer traps instead of hanging the GPU
+        }
     }
     __syncthreads();
     // (3) sum the slots in rank order: deterministic and bit-identical on every rank
@@ -128,6 +132,14 @@ int ctvq_peer_allreduce(void* const* peer_bufs, int world, int rank, size_t coun
     int prev = -1;
     cudaGetDevice(&prev);
     if (prev != device) cudaSetDevice(device);
+    // same shared-memory carve-out as the quantiser kernels (which take ~210 KB per SM): an SM configured for a small
+    // carve-out would have to drain and reconfigure before it can host the next forward's CTA, i.e. in overlap mode the
+    // forward would wait for this kernel's handshake on those SMs
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        cudaFuncSetAttribute(peer_allreduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
     size_t blocks = (count + 512 * 4 - 1) / (512 * 4);
     if (blocks < 1) blocks = 1;
     if (blocks > 148) blocks = 148;
