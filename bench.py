@@ -420,7 +420,7 @@ def main():
     ]
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full capture
     # of this very workload (profiles/r1_fwd_ws_b16384.md); only quoted for the profiled batch size
-    ncu_traffic = {16384: (146880768 + 510873344, 717345280 + 497457664)}.get(B)
+    ncu_traffic = {16384: (146883328 + 511268352, 717339648 + 497255936)}.get(B)
     for i, k in enumerate(kernels):
         k["frac"] = k["gbs"] / peak
         k["traffic"] = ncu_traffic[i] if ncu_traffic else None
