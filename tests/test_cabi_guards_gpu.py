@@ -27,7 +27,11 @@ SHAPES = [
     # B, Dtot, H, W, C, d, K, chan_stride, path
     (6, 128, 8, 8, 4, 32, 64, 1, "auto"),     # config 2: specialised tcgen05 forward + fast backward
     (700, 128, 8, 8, 4, 32, 64, 1, "auto"),   # ... large enough for the TMA-ring backward (N >= 37888)
-    (3, 64, 16, 16, 1, 64, 512, 1, "auto"),   # config 1: single-codebook kernel, two rounds
+    (3, 64, 16, 16, 1, 64, 512, 1, "auto"),   # config 1: streaming single-codebook kernel (8 units of 64 codes)
+    (5, 32, 8, 8, 1, 32, 300, 1, "auto"),     # streaming kernel, d=32 (4 teams), ragged last unit, partial super-tile
+    (9, 128, 8, 8, 1, 128, 200, 1, "auto"),   # streaming kernel, d=128 (2 teams, rows re-read from the slab)
+    (3, 256, 4, 8, 1, 256, 100, 1, "auto"),   # streaming kernel, d=256 (1 team)
+    (1200, 64, 8, 8, 1, 64, 128, 1, "auto"),  # large enough for the single-codebook shared-atomic backward
     (5, 128, 8, 8, 1, 128, 64, 1, "auto"),    # config 3
     (3, 48, 8, 4, 2, 24, 50, 24, "auto"),     # generic tcgen05 kernel (K padded to 64, HW = 32)
     (2, 15, 3, 3, 5, 3, 7, 1, "auto"),        # ragged: SIMT + direct-atomic backward
