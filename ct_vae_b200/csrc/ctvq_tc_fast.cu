@@ -34,7 +34,17 @@ __device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT, 2 ulp: in
 struct FastParams {
     QuantParams q;
     int ntiles;
+    unsigned long long* trace;  // debug: 8 globaltimer stamps per CTA (null in production), ctvq_debug_set_fast_trace()
 };
+unsigned long long* g_fast_trace = nullptr;
+
+__device__ __forceinline__ void stamp(const FastParams& P, int slot) {
+    if (P.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.trace[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ void or_if_ge(unsigned& m, float a, float lim, unsigned bit) {
     asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(a), "f"(lim), "r"(bit));
@@ -51,6 +61,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     const QuantParams& p = P.q;
     const int K = p.K;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quarter = warp & 3, wg = warp >> 2;
+    if (tid == 0) stamp(P, 0);
     constexpr int kFT = 128 * NWG + 32;                // NWG epilogue warpgroups + the producer warp
     constexpr int USEDP = ((C - 1) * CS + D + 7) / 8 * 8;
     constexpr int DJB = (D + 31) / 32;
@@ -88,6 +99,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     }
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
     __syncthreads();  // barriers initialised before the first TMA may signal them
+    if (tid == 0) stamp(P, 1);
 
     const int niter = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const bool producer = (tid == 128 * NWG);
@@ -174,6 +186,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     if (tid < C) emax_s[tid] = sqrtf(__uint_as_float(reinterpret_cast<unsigned*>(emax_s)[tid])) * 1.0001f;
     const uint32_t tmem_base = *tmem_slot;
     __syncthreads();
+    if (tid == 0) stamp(P, 2);
 
     float lsum[C];
 #pragma unroll
@@ -232,6 +245,8 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
             const int hw = (int)(n - b * HWT);
             const int st = it % NSTAGE, buf = it & 1;
             mbar_wait_fast(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
+            if (tid == 0 && u == 0) stamp(P, 3);    // first slab landed
+            if (tid == 0 && u == NWG) stamp(P, 4);  // first unit of this warp finished
             // this thread's row, every channel of its codebook, read from shared memory ONCE into registers
             const uint8_t* zblk = a_s + st * kStage + quarter * kBlk + c * CS * 128;
             float zr[D];
@@ -366,6 +381,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
             }
         }
     }
+    if (tid == 0) stamp(P, 5);  // this warp's last unit done
     // ---- loss: warp sums -> fp64 atomics -> last CTA finalises -----------------------------------------------------
     if (p.fused) {
         if (warp < 4 * NWG) {
@@ -400,6 +416,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) stamp(P, 6);
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -409,6 +426,7 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
     P.q = p0;
     P.q.tiles_per_seg = (int)((p0.N + kTM - 1) / kTM);
     P.ntiles = P.q.tiles_per_seg * p0.n_seg;
+    P.trace = g_fast_trace;
     constexpr int USEDP = ((C - 1) * CS + D + 7) / 8 * 8;
     constexpr int DJB = (D + 31) / 32;
     Maps maps;
@@ -426,6 +444,8 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
 }
 
 }  // namespace
+
+extern "C" void ctvq_debug_set_fast_trace(unsigned long long* buf) { g_fast_trace = buf; }  // [148*8] device words or null
 
 // Shapes with a specialised kernel; anything else falls through to the generic tcgen05 kernel / SIMT.
 int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
