@@ -56,14 +56,6 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
         }
     }
 }
-// Control-lane wait: tight spin (no sleep hint) so a single producer / MMA lane reacts within a few cycles of the
-// phase flip; ~2 s of polling traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-#pragma unroll 1
-    for (unsigned it = 0; it < (1u << 28); ++it)
-        if (mbar_try_wait(bar, parity)) return;
-    __trap();
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -168,24 +160,6 @@ __device__ __forceinline__ uint32_t e_off(int k, int j, int Kpad) {
     return (uint32_t)((j >> 5) * Kpad * 128 + k * 128 + (((((j & 31) >> 2) ^ (k & 7)) & 7) << 4) + ((j & 3) << 2));
 }
 
-
-// Packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2): two independent round-to-nearest operations per instruction,
-// bit-identical to the scalar forms — halves the issue slots of the element-wise epilogue math.
-__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-    unsigned long long a, b, c, d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
-}
-__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    unsigned long long a, b, d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
-}
 
 struct Maps {
     CUtensorMap m[CTVQ_MAX_SEGMENTS];
