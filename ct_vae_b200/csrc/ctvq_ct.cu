@@ -77,34 +77,52 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ x
 }
 
 // latent_CrossEntropy_loss forward: per row  log(sum_k x'_k) - log(x'_t),  x' = max(x, 1e-4),  t = argmax_k y;  mean over
-// the B*S rows.  Writes the targets (for the backward) and the per-row sum of x'.
+// the B*S rows.  Writes the targets (for the backward) and the per-row sum of x'.  VEC rows per thread (128-bit loads).
+__device__ __forceinline__ float clamp_min_keep_nan(float x) { return x != x ? x : fmaxf(x, 1e-4f); }  // torch.clamp keeps NaN
+
+template <int VEC>
 __global__ void __launch_bounds__(256) latent_ce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                             long long B, long long S, int K, long long* __restrict__ tgt,
                                                             float* __restrict__ rowsum, float* loss_out, double* acc,
                                                             unsigned int* ticket) {
     __shared__ double red[32];
     double part = 0.0;
-    const long long total = B * S;
+    const long long groups = S / VEC;
+    const long long total = B * groups;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long b = i / S, s = i - b * S;
+        const long long b = i / groups, s = (i - b * groups) * VEC;
         const float* xs = x + (size_t)b * K * S + s;
         const float* ys = y + (size_t)b * K * S + s;
-        float best = __ldg(ys);
-        int t = 0;
-        float sum = fmaxf(__ldg(xs), 1e-4f), xt = sum;
-        // clamp(min) keeps NaN (torch.clamp propagates it): fmaxf would drop it, so test explicitly
-        if (__ldg(xs) != __ldg(xs)) { sum = __ldg(xs); xt = sum; }
+        float best[VEC], sum[VEC], xt[VEC];
+        int t[VEC];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) { best[u] = 0.0f; sum[u] = 0.0f; xt[u] = 0.0f; t[u] = 0; }
 #pragma unroll 4
-        for (int c = 1; c < K; ++c) {
-            const float yv = __ldg(ys + (size_t)c * S);
-            const float xr = __ldg(xs + (size_t)c * S);
-            const float xv = xr != xr ? xr : fmaxf(xr, 1e-4f);
-            sum += xv;
-            if (yv > best || (yv != yv && best == best)) { best = yv; t = c; xt = xv; }
+        for (int c = 0; c < K; ++c) {
+            float yv[VEC], xr[VEC];
+            if (VEC == 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(ys + (size_t)c * S));
+                const float4 q = __ldg(reinterpret_cast<const float4*>(xs + (size_t)c * S));
+                yv[0] = a.x; yv[1 % VEC] = a.y; yv[2 % VEC] = a.z; yv[3 % VEC] = a.w;
+                xr[0] = q.x; xr[1 % VEC] = q.y; xr[2 % VEC] = q.z; xr[3 % VEC] = q.w;
+            } else {
+                yv[0] = __ldg(ys + (size_t)c * S);
+                xr[0] = __ldg(xs + (size_t)c * S);
+            }
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) {
+                const float xv = clamp_min_keep_nan(xr[u]);
+                sum[u] += xv;
+                // torch.argmax: first maximum wins, the first NaN wins over any number
+                if (c == 0 || yv[u] > best[u] || (yv[u] != yv[u] && best[u] == best[u])) { best[u] = yv[u]; t[u] = c; xt[u] = xv; }
+            }
         }
-        tgt[i] = t;
-        rowsum[i] = sum;
-        part += (double)(logf(sum) - logf(xt));
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            tgt[b * S + s + u] = t[u];
+            rowsum[b * S + s + u] = sum[u];
+            part += (double)(logf(sum[u]) - logf(xt[u]));
+        }
     }
     // block reduce -> fp64 atomic -> last block finalises
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -121,7 +139,7 @@ __global__ void __launch_bounds__(256) latent_ce_fwd_kernel(const float* __restr
             __threadfence();
             if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
                 __threadfence();
-                *loss_out = (float)(__ldcg(acc) / (double)total);
+                *loss_out = (float)(__ldcg(acc) / (double)(B * S));
                 *acc = 0.0;
                 *ticket = 0u;
                 __threadfence();
@@ -131,23 +149,41 @@ __global__ void __launch_bounds__(256) latent_ce_fwd_kernel(const float* __restr
 }
 
 // d loss / d x[b,k,s] = g/R * [x >= 1e-4] * (1/sum' - [k == t]/x'_t)      (clamp(min) passes gradient where x >= min)
+template <int VEC>
 __global__ void __launch_bounds__(256) latent_ce_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ tgt,
                                                             const float* __restrict__ rowsum, const float* __restrict__ g_loss,
                                                             long long B, long long S, int K, float* __restrict__ gx) {
-    const long long total = B * S;
-    const float g = __ldg(g_loss) / (float)total;
+    const long long groups = S / VEC;
+    const long long total = B * groups;
+    const float g = __ldg(g_loss) / (float)(B * S);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long b = i / S, s = i - b * S;
+        const long long b = i / groups, s = (i - b * groups) * VEC;
         const float* xs = x + (size_t)b * K * S + s;
         float* gs = gx + (size_t)b * K * S + s;
-        const int t = (int)__ldg(tgt + i);
-        const float inv = 1.0f / __ldg(rowsum + i);
+        int t[VEC];
+        float inv[VEC];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            t[u] = (int)__ldg(tgt + b * S + s + u);
+            inv[u] = 1.0f / __ldg(rowsum + b * S + s + u);
+        }
 #pragma unroll 4
         for (int c = 0; c < K; ++c) {
-            const float xr = __ldg(xs + (size_t)c * S);
-            float d = inv;
-            if (c == t) d -= 1.0f / fmaxf(xr, 1e-4f);
-            gs[(size_t)c * S] = xr >= 1e-4f ? g * d : 0.0f;
+            float xr[VEC], o[VEC];
+            if (VEC == 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(xs + (size_t)c * S));
+                xr[0] = q.x; xr[1 % VEC] = q.y; xr[2 % VEC] = q.z; xr[3 % VEC] = q.w;
+            } else {
+                xr[0] = __ldg(xs + (size_t)c * S);
+            }
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) {
+                float d = inv[u];
+                if (c == t[u]) d -= 1.0f / fmaxf(xr[u], 1e-4f);
+                o[u] = xr[u] >= 1e-4f ? g * d : 0.0f;
+            }
+            if (VEC == 4) *reinterpret_cast<float4*>(gs + (size_t)c * S) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+            else gs[(size_t)c * S] = o[0];
         }
     }
 }
@@ -176,13 +212,17 @@ int launch_class_argmax(const float* x, long long B, long long S, int K, long lo
 
 int launch_latent_ce_fwd(const float* x, const float* y, long long B, long long S, int K, long long* tgt, float* rowsum,
                          float* loss, Workspace* ws, cudaStream_t s) {
-    latent_ce_fwd_kernel<<<grid_for(B * S), 256, 0, s>>>(x, y, B, S, K, tgt, rowsum, loss, &ws->kld_acc, &ws->ticket2);
+    const bool vec = (S % 4 == 0) && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15);
+    if (vec) latent_ce_fwd_kernel<4><<<grid_for(B * (S / 4)), 256, 0, s>>>(x, y, B, S, K, tgt, rowsum, loss, &ws->kld_acc, &ws->ticket2);
+    else latent_ce_fwd_kernel<1><<<grid_for(B * S), 256, 0, s>>>(x, y, B, S, K, tgt, rowsum, loss, &ws->kld_acc, &ws->ticket2);
     return (int)cudaGetLastError();
 }
 
 int launch_latent_ce_bwd(const float* x, const long long* tgt, const float* rowsum, const float* g_loss, long long B,
                          long long S, int K, float* gx, cudaStream_t s) {
-    latent_ce_bwd_kernel<<<grid_for(B * S), 256, 0, s>>>(x, tgt, rowsum, g_loss, B, S, K, gx);
+    const bool vec = (S % 4 == 0) && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gx)) & 15);
+    if (vec) latent_ce_bwd_kernel<4><<<grid_for(B * (S / 4)), 256, 0, s>>>(x, tgt, rowsum, g_loss, B, S, K, gx);
+    else latent_ce_bwd_kernel<1><<<grid_for(B * S), 256, 0, s>>>(x, tgt, rowsum, g_loss, B, S, K, gx);
     return (int)cudaGetLastError();
 }
 
