@@ -21,18 +21,20 @@ __device__ __forceinline__ void half_sync(int half) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(kHT) : "memory");
 }
 
-// TM: rows per tile (per half)
-template <int TM>
+// TM: rows per tile (per half); GACC: the [K, d] accumulator does not fit in shared memory -> the (channel-coalesced,
+// 128 bytes per warp) atomics go straight to grad_E in L2: with thousands of codes the rows rarely collide
+template <int TM, bool GACC>
 __global__ void __launch_bounds__(2 * kHT) vq_bwd_c1_kernel(const BwdParams p, const int ntiles) {
     extern __shared__ __align__(16) float smem[];
     const int d = p.d, K = p.K, HW = p.HW;
     constexpr int ZS = TM + 1;  // odd stride: conflict-free with lanes along rows (staging, grad_z) and along channels (accumulate)
     const int kd = K * d;
     const int tid = threadIdx.x, half = tid / kHT, ht = tid % kHT, lane = ht & 31, hw_ = ht >> 5;  // hw_: warp within the half
-    float* acc = smem;                                         // [K][d], shared by both halves
-    float* zd = acc + kd + (size_t)half * ((size_t)d * ZS + TM);  // [d][ZS]: z, then q - z in place
+    float* acc = smem;                                         // [K][d], shared by both halves (absent when GACC)
+    float* zd = acc + (GACC ? 0 : kd) + (size_t)half * ((size_t)d * ZS + TM);  // [d][ZS]: z, then q - z in place
     int* idx_s = reinterpret_cast<int*>(zd + (size_t)d * ZS);  // [TM]
-    for (int i = tid; i < kd; i += 2 * kHT) acc[i] = 0.0f;
+    if (!GACC)
+        for (int i = tid; i < kd; i += 2 * kHT) acc[i] = 0.0f;
     const float gl = __ldg(p.g_loss);
     const double nd = (double)p.N * (double)d;
     const float coef_e = (float)(2.0 / nd) * gl;                    // weight of (q - z) in d vq_loss / d E
@@ -105,7 +107,8 @@ __global__ void __launch_bounds__(2 * kHT) vq_bwd_c1_kernel(const BwdParams p, c
                         if (k[u] >= 0) {
                             const int m = m0 + u * (kHT / 32);
                             const float diff = __fsub_rn(e[u], zd[j * ZS + m]);  // q - z
-                            atomicAdd(acc + (size_t)k[u] * d + j, diff);
+                            if (GACC) atomicAdd(p.gE + (size_t)k[u] * d + j, coef_e * diff);
+                            else atomicAdd(acc + (size_t)k[u] * d + j, diff);
                             zd[j * ZS + m] = diff;
                         }
                     }
@@ -134,20 +137,22 @@ __global__ void __launch_bounds__(2 * kHT) vq_bwd_c1_kernel(const BwdParams p, c
             *reinterpret_cast<float4*>(p.gz + off) = g;
         }
     }
-    __syncthreads();
-    for (int i = tid; i < kd; i += 2 * kHT) {
-        const float v = acc[i];
-        if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
+    if (!GACC) {
+        __syncthreads();
+        for (int i = tid; i < kd; i += 2 * kHT) {
+            const float v = acc[i];
+            if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
+        }
     }
 }
 
-template <int TM>
+template <int TM, bool GACC>
 int launch_c1(const BwdParams& p, size_t sm, int per_sm, int ntiles, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(vq_bwd_c1_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaError_t e = cudaFuncSetAttribute(vq_bwd_c1_kernel<TM, GACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;
     int grid = 148 * per_sm;
     if (grid * 2 > ntiles) grid = (ntiles + 1) / 2;
-    vq_bwd_c1_kernel<TM><<<grid, 2 * kHT, sm, s>>>(p, ntiles);
+    vq_bwd_c1_kernel<TM, GACC><<<grid, 2 * kHT, sm, s>>>(p, ntiles);
     return (int)cudaGetLastError();
 }
 }  // namespace
@@ -160,20 +165,32 @@ int launch_backward_c1(const BwdParams& p, cudaStream_t s) {
     if (reinterpret_cast<uintptr_t>(p.z) & 15) return CTVQ_E_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(p.gz) & 15) || (p.g_out && (reinterpret_cast<uintptr_t>(p.g_out) & 15))) return CTVQ_E_UNSUPPORTED;
     const size_t kd = (size_t)p.K * p.d;
-    auto bytes = [&](int TM) { return (kd + 2 * ((size_t)p.d * (TM + 1) + TM)) * sizeof(float); };
+    auto bytes = [&](int TM, bool gacc) { return ((gacc ? 0 : kd) + 2 * ((size_t)p.d * (TM + 1) + TM)) * sizeof(float); };
+    const long long nrows = p.N;
+    bool gacc = false;
     int TM = 128;
-    if (bytes(128) > 220 * 1024) TM = 64;
-    if (bytes(TM) > 220 * 1024) return CTVQ_E_UNSUPPORTED;
-    const size_t sm = bytes(TM);
+    if (bytes(128, false) > 220 * 1024) TM = 64;
+    if (bytes(TM, false) > 220 * 1024) {  // accumulator too big for shared memory: atomics straight to grad_E
+        gacc = true;
+        TM = bytes(128, true) <= 220 * 1024 ? 128 : 64;
+        if (bytes(TM, true) > 220 * 1024) return CTVQ_E_UNSUPPORTED;
+        if (p.K < 256) return CTVQ_E_UNSUPPORTED;  // few codes: global atomics on the same rows would serialise
+    }
+    const size_t sm = bytes(TM, gacc);
     int per_sm = (int)((227 * 1024) / (sm + 1024));
     if (per_sm > 2) per_sm = 2;  // 2 x 512 threads fill the SM
     if (per_sm < 1) per_sm = 1;
-    const long long ntiles_ll = (p.N + TM - 1) / TM;
+    const long long ntiles_ll = (nrows + TM - 1) / TM;
     if (ntiles_ll > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
-    // every CTA zeroes and flushes a [K,d] accumulator: only worth it when the rows outweigh that
-    const long long ctas = (ntiles_ll + 1) / 2 < 148LL * per_sm ? (ntiles_ll + 1) / 2 : 148LL * per_sm;
-    if ((double)p.N * p.d < 2.0 * (double)ctas * (double)kd) return CTVQ_E_UNSUPPORTED;
-    return TM == 128 ? launch_c1<128>(p, sm, per_sm, (int)ntiles_ll, s) : launch_c1<64>(p, sm, per_sm, (int)ntiles_ll, s);
+    if (!gacc) {
+        // every CTA zeroes and flushes a [K,d] accumulator: only worth it when the rows outweigh that
+        const long long ctas = (ntiles_ll + 1) / 2 < 148LL * per_sm ? (ntiles_ll + 1) / 2 : 148LL * per_sm;
+        if ((double)p.N * p.d < 2.0 * (double)ctas * (double)kd) return CTVQ_E_UNSUPPORTED;
+    } else if (p.N < 32768) {
+        return CTVQ_E_UNSUPPORTED;  // tiny batches keep the direct kernel
+    }
+    if (gacc) return TM == 128 ? launch_c1<128, true>(p, sm, per_sm, (int)ntiles_ll, s) : launch_c1<64, true>(p, sm, per_sm, (int)ntiles_ll, s);
+    return TM == 128 ? launch_c1<128, false>(p, sm, per_sm, (int)ntiles_ll, s) : launch_c1<64, false>(p, sm, per_sm, (int)ntiles_ll, s);
 }
 
 }  // namespace ctvq

@@ -144,6 +144,8 @@ def test_non_finite_rows_follow_torch_argmin(env, path, shape):
     ("bwd_d64_k512_cfg1_codebook", 1024, 64, 16, 16, 512),     # configs/vq_vae.yaml at B=1024
     ("bwd_d128_k256_tm64", 2048, 128, 8, 8, 256),              # accumulator leaves room for 64-row tiles only
     ("bwd_d64_k200_ragged", 515, 64, 8, 8, 200),               # last tile partial, K not a power of two
+    ("bwd_d64_k1024_global_acc", 128, 64, 16, 16, 1024),       # [K,d] exceeds shared memory: coalesced atomics to grad_E
+    ("bwd_d256_k256_global_acc", 130, 256, 16, 16, 256),
 ])
 def test_single_codebook_backward_at_scale(env, cfg):
     """grad_z and the codebook-gradient scatter-add against the C oracle at sizes where the
