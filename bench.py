@@ -286,7 +286,7 @@ def main():
             try:
                 # overlap: the all-reduce of step i runs on a side stream underneath the forward of step i+1 (its result is
                 # only needed by the optimizer); every timed region ends with comm.wait(), so all of them are inside it
-                comm = PeerGradComm(CFG["C"] * CFG["K"] * (CFG["D"] // CFG["C"]), dev, overlap=True)
+                comm = PeerGradComm(CFG["C"] * CFG["K"] * (CFG["D"] // CFG["C"]), dev, overlap=os.environ.get("CTVQ_PEER_OVERLAP", "1") != "0")
             except Exception as e:  # no CUDA IPC / peer access on this box: NCCL carries the collective instead
                 print(f"[bench] peer collective unavailable ({e!r}); using NCCL", file=sys.stderr)
                 collective = "nccl"

@@ -2,6 +2,7 @@
 // Replaces the NCCL call for the path's only collective when every rank sits on one NVSwitch box: the message is
 // 32 KB (latency-bound), so each rank simply reads all peers' slots through P2P-mapped pointers and sums them in
 // rank order after a flag handshake — one kernel, no second barrier (slots alternate by epoch parity).
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctvq_common.cuh"
@@ -140,10 +141,15 @@ int ctvq_peer_allreduce(void* const* peer_bufs, int world, int rank, size_t coun
         cudaFuncSetAttribute(peer_allreduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carveout_set = true;
     }
-    size_t blocks = (count + 512 * 4 - 1) / (512 * 4);
+    // SMALL CTAs: in overlap mode this kernel must co-reside with the next forward's 544-thread, 96-register CTA on the
+    // same SMs.  Measured at N=2: 512-thread CTAs delay the forward by 9 us (0.173 vs 0.164 ms), 64-thread CTAs do not.
+    static const int threads = [] { const char* e = getenv("CTVQ_PEER_THREADS"); const int t = e ? atoi(e) : 64; return t >= 32 && t <= 512 ? t : 64; }();
+    size_t blocks = (count + (size_t)threads * 32 - 1) / ((size_t)threads * 32);
     if (blocks < 1) blocks = 1;
     if (blocks > 148) blocks = 148;
-    peer_allreduce_kernel<<<(unsigned)blocks, 512, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    static const int max_blocks = [] { const char* e = getenv("CTVQ_PEER_BLOCKS"); return e ? atoi(e) : 148; }();
+    if (max_blocks >= 1 && blocks > (size_t)max_blocks) blocks = (size_t)max_blocks;
+    peer_allreduce_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
     const int rc = (int)cudaGetLastError();
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
     return rc;
