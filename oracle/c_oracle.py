@@ -79,3 +79,32 @@ def reparam_kld(mu, logvar, eps):
     k = torch.empty(1)
     lib().ctvq_c_reparam_kld(_f(mu), _f(logvar), _f(eps), ctypes.c_int64(mu.shape[0]), mu.shape[1], _f(z), _f(k))
     return z, k[0]
+
+
+# ---- CT-mode codec (models/ct_mcq_vae.py:472-496, 306-311): tensors as [B, K, S] / [B, S] like the kernels -----------
+def ct_onehot(inds: torch.Tensor, num_embeddings: int) -> torch.Tensor:
+    """[B, C, H, W] int64 -> one-hot fp32 [B, N, C*H, W] (contiguous)."""
+    b, c, h, w = inds.shape
+    idx = inds.contiguous()
+    out = torch.empty(b, num_embeddings, c * h, w)
+    lib().ctvq_c_onehot(_f(idx), ctypes.c_int64(b), ctypes.c_int64(c * h * w), num_embeddings, _f(out))
+    return out
+
+
+def ct_class_argmax(scores: torch.Tensor, codebooks: int) -> torch.Tensor:
+    """[B, N, C*H, W] fp32 -> [B, C, H, W] int64."""
+    x = scores.detach().contiguous().float()
+    b, n, ch, w = x.shape
+    out = torch.empty(b, codebooks, ch // codebooks, w, dtype=torch.int64)
+    lib().ctvq_c_class_argmax(_f(x), ctypes.c_int64(b), ctypes.c_int64(ch * w), n, _f(out))
+    return out
+
+
+def ct_latent_ce(latent: torch.Tensor, latent_y: torch.Tensor, g: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(loss, d loss*g / d latent) of latent_CrossEntropy_loss."""
+    x, y = latent.detach().contiguous().float(), latent_y.detach().contiguous().float()
+    b, n, ch, w = x.shape
+    loss = torch.empty(())
+    gx = torch.empty_like(x)
+    lib().ctvq_c_latent_ce(_f(x), _f(y), ctypes.c_int64(b), ctypes.c_int64(ch * w), n, ctypes.c_float(g), _f(loss), _f(gx))
+    return loss, gx

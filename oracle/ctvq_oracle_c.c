@@ -110,3 +110,60 @@ void ctvq_c_reparam_kld(const float *mu, const float *lv, const float *eps, int6
     }
     *kld_out = (float)(-0.5 * acc / (double)B);
 }
+
+/* ---- CT-mode codec, same layouts as the kernels: one-hots / scores fp32 [B, K, S] contiguous
+ * (S = C*H*W), indices int64 [B, S] ------------------------------------------------------------------------------ */
+
+/* CTMCQVAE.ct_preprocess, models/ct_mcq_vae.py:472-483 (F.one_hot + view + permute, made contiguous) */
+void ctvq_c_onehot(const int64_t *idx, int64_t B, int64_t S, int K, float *out) {
+    for (int64_t b = 0; b < B; ++b)
+        for (int k = 0; k < K; ++k)
+            for (int64_t s = 0; s < S; ++s) out[(b * K + k) * S + s] = idx[b * S + s] == k ? 1.0f : 0.0f;
+}
+
+/* CTMCQVAE.ct_postprocess, models/ct_mcq_vae.py:485-496: torch.argmax over the class dimension
+ * (first maximum wins; the first NaN wins over any number) */
+void ctvq_c_class_argmax(const float *x, int64_t B, int64_t S, int K, int64_t *idx) {
+    for (int64_t b = 0; b < B; ++b)
+        for (int64_t s = 0; s < S; ++s) {
+            float best = x[(b * K) * S + s];
+            int bi = 0;
+            for (int k = 1; k < K; ++k) {
+                const float v = x[(b * K + k) * S + s];
+                if (v > best || (v != v && best == best)) { best = v; bi = k; }
+            }
+            idx[b * S + s] = bi;
+        }
+}
+
+/* CausalTransition.latent_CrossEntropy_loss, models/ct_mcq_vae.py:306-311, and its gradient w.r.t. latent:
+ *   loss = mean_rows( log(sum_k x'_k) - log(x'_t) ),  x' = max(x, 1e-4),  t = argmax_k y
+ *   g_x[b,k,s] = g / R * [x >= 1e-4] * (1/sum' - [k == t]/x'_t)
+ * Sums in double (the checker wants the exact value; the kernels are held to 1e-5 relative). */
+void ctvq_c_latent_ce(const float *x, const float *y, int64_t B, int64_t S, int K, float g, float *loss_out, float *gx) {
+    const double R = (double)B * (double)S;
+    double total = 0.0;
+    for (int64_t b = 0; b < B; ++b)
+        for (int64_t s = 0; s < S; ++s) {
+            float best = y[(b * K) * S + s];
+            int t = 0;
+            double sum = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const float xv = x[(b * K + k) * S + s];
+                sum += (double)(xv != xv ? xv : (xv > 1e-4f ? xv : 1e-4f));
+                const float yv = y[(b * K + k) * S + s];
+                if (k > 0 && (yv > best || (yv != yv && best == best))) { best = yv; t = k; }
+            }
+            const float xt_raw = x[(b * K + t) * S + s];
+            const double xt = (double)(xt_raw != xt_raw ? xt_raw : (xt_raw > 1e-4f ? xt_raw : 1e-4f));
+            total += log(sum) - log(xt);
+            if (gx)
+                for (int k = 0; k < K; ++k) {
+                    const float xv = x[(b * K + k) * S + s];
+                    double d = 1.0 / sum;
+                    if (k == t) d -= 1.0 / xt;
+                    gx[(b * K + k) * S + s] = xv >= 1e-4f ? (float)((double)g / R * d) : 0.0f;
+                }
+        }
+    *loss_out = (float)(total / R);
+}

@@ -102,3 +102,19 @@ def test_ct_codec_install_rebinds_reference_methods():
     a, b = types.SimpleNamespace(), types.SimpleNamespace()
     ct_codec.install(a, b)
     assert callable(a.ct_preprocess) and callable(a.ct_postprocess) and callable(b.latent_CrossEntropy_loss)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_c_oracle_matches_reference_golden(name):
+    """The plain-C restatement of the codec (oracle/ctvq_oracle_c.c) against the live-reference goldens: converters
+    bit-exact, loss / gradient to 1e-6 (the C oracle sums in double, the reference in fp32)."""
+    from oracle import c_oracle as CO
+    g = _load(name)
+    N, C = int(g["N"]), int(g["C"])
+    assert torch.equal(CO.ct_onehot(g["inds"], N), g["onehot"])
+    assert torch.equal(CO.ct_class_argmax(g["scores"], C), g["post"])
+    assert torch.equal(CO.ct_class_argmax(g["onehot"], C), g["inds"])
+    loss, gx = CO.ct_latent_ce(g["latent"], g["latent_y"], float(g["g_ce"]))
+    assert rel_err(loss, g["ce"]) < 1e-6
+    assert rel_err(gx, g["g_latent"]) < 1e-6
+    assert torch.equal(gx == 0, g["g_latent"] == 0)
