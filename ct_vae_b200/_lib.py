@@ -3,6 +3,7 @@ tensor is not on a CUDA device the ops raise."""
 import ctypes
 import os
 import threading
+from typing import Optional
 
 import torch
 
@@ -21,9 +22,10 @@ _SIGNATURES = {
     "ctvq_workspace_bytes": (_sz, [_i, _i, _i]),
     "ctvq_set_path": (_i, [_i]),
     "ctvq_last_path": (_i, []),
-    "ctvq_argmin": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_read_and_clear_err": (_i, [_vp, _sz, ctypes.POINTER(ctypes.c_uint), _i, _vp]),
+    "ctvq_argmin": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "ctvq_gather_st_loss": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _i, _vp]),
-    "ctvq_forward": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_forward": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "ctvq_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _i, _vp]),
     "ctvq_reparam_kld_fwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "ctvq_reparam_kld_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp]),
@@ -92,6 +94,49 @@ def workspace(device: torch.device, stream_ptr: int, c: int = 0, k: int = 0, d: 
         ws = torch.zeros(max(n, 4096), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+_validate = os.environ.get("CTVQ_VALIDATE", "0") not in ("", "0")
+
+
+def set_validate(on: bool) -> bool:
+    """Debug switch (also env CTVQ_VALIDATE=1): after every op that consumes caller-supplied indices, read the
+    error word back (one stream synchronisation per call) and raise IndexError like the reference's ``scatter_`` /
+    ``F.one_hot`` do (models/vq_vae.py:40, models/ct_mcq_vae.py:480).  Returns the previous setting."""
+    global _validate
+    prev, _validate = _validate, bool(on)
+    return prev
+
+
+def validating() -> bool:
+    return _validate
+
+
+def read_and_clear_err(ws: torch.Tensor, device: torch.device, sp: int) -> int:
+    word = ctypes.c_uint(0)
+    check(lib().ctvq_read_and_clear_err(ws.data_ptr(), ws.numel(), ctypes.byref(word), device.index, sp),
+          "ctvq_read_and_clear_err")
+    return int(word.value)
+
+
+def raise_if_bad_indices(device: Optional[torch.device] = None) -> None:
+    """Explicit check point (synchronises): raises IndexError when any op on ``device`` (default: every device) met an
+    index outside [0, K) since the last check.  The kernels clamp such indices instead of faulting."""
+    bad = []
+    for (idx, sp), ws in list(_workspaces.items()):
+        if device is not None and device.index != idx:
+            continue
+        if read_and_clear_err(ws, torch.device("cuda", idx), sp):
+            bad.append(idx)
+    if bad:
+        raise IndexError(f"ct_vae_b200: code index out of range [0, K) on cuda device(s) {sorted(set(bad))} "
+                         "(the reference raises from scatter_/F.one_hot; the kernels clamped it)")
+
+
+def maybe_validate(ws: torch.Tensor, device: torch.device, sp: int, what: str) -> None:
+    if _validate and read_and_clear_err(ws, device, sp):
+        raise IndexError(f"{what}: code index out of range [0, K) (clamped by the kernel; the reference raises from "
+                         "scatter_/F.one_hot)")
 
 
 def stream_ptr(device: torch.device) -> int:

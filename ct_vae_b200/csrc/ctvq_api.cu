@@ -101,12 +101,26 @@ size_t ctvq_workspace_bytes(int C, int K, int d) {
     return C == 1 && K > 0 ? kScratchOffset + stream_scratch_bytes(K) : kScratchOffset;
 }
 
+int ctvq_read_and_clear_err(void* workspace, size_t ws_bytes, unsigned* err_out_host, int device, void* stream) {
+    if (!workspace || !err_out_host) return CTVQ_E_BADARG;
+    if (ws_bytes < sizeof(Workspace)) return CTVQ_E_WORKSPACE;
+    DeviceGuard g(device);
+    if (g.err != cudaSuccess) return (int)g.err;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned int* err = &static_cast<Workspace*>(workspace)->err;
+    cudaError_t e = cudaMemcpyAsync(err_out_host, err, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(err, 0, sizeof(unsigned), s);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize(s);
+}
+
 int ctvq_set_path(int path) { return g_path.exchange(path); }
 int ctvq_last_path(void) { return t_last_path; }
 
 int ctvq_argmin(const void* const* z_segs, int n_seg, const void* const* codebooks, int64_t B, int Dtot, int HW, int C,
-                int d, int K, int chan_stride, int dtype, int64_t* const* idx_out_segs, void* workspace,
-                size_t ws_bytes, int device, void* stream) {
+                int d, int K, int chan_stride, int dtype, int64_t* const* idx_out_segs,
+                unsigned long long* neartie_count_out, void* workspace, size_t ws_bytes, int device, void* stream) {
     if (!z_segs || !idx_out_segs || n_seg < 1 || n_seg > CTVQ_MAX_SEGMENTS) return CTVQ_E_BADARG;
     int rc = check_shape(B, Dtot, HW, C, d, K, chan_stride, dtype);
     if (rc) return rc;
@@ -120,6 +134,7 @@ int ctvq_argmin(const void* const* z_segs, int n_seg, const void* const* codeboo
         p.idx[s] = reinterpret_cast<long long*>(idx_out_segs[s]);
     }
     p.fused = 0;
+    p.neartie = neartie_count_out;
     DeviceGuard g(device);
     if (g.err != cudaSuccess) return (int)g.err;
     return dispatch_forward(p, static_cast<cudaStream_t>(stream));
@@ -147,7 +162,7 @@ int ctvq_gather_st_loss(const void* z, const void* const* codebooks, const int64
 
 int ctvq_forward(const void* z, const void* const* codebooks, int64_t B, int Dtot, int HW, int C, int d, int K,
                  int chan_stride, int dtype, float beta, int64_t* idx_out, void* q_out, float* loss_out,
-                 void* workspace, size_t ws_bytes, int device, void* stream) {
+                 unsigned long long* neartie_count_out, void* workspace, size_t ws_bytes, int device, void* stream) {
     if (!z || !idx_out || !q_out || !loss_out) return CTVQ_E_BADARG;
     int rc = check_shape(B, Dtot, HW, C, d, K, chan_stride, dtype);
     if (rc) return rc;
@@ -160,6 +175,7 @@ int ctvq_forward(const void* z, const void* const* codebooks, int64_t B, int Dto
     p.loss_out = loss_out;
     p.beta = beta;
     p.fused = 1;
+    p.neartie = neartie_count_out;
     DeviceGuard g(device);
     if (g.err != cudaSuccess) return (int)g.err;
     return dispatch_forward(p, static_cast<cudaStream_t>(stream));

@@ -26,7 +26,19 @@ struct QuantParams {
     int fused;  // 0: argmin only, 1: argmin + gather + loss
     unsigned char* scratch;  // optional per-stream scratch behind the Workspace header (256-byte aligned), may be null
     size_t scratch_bytes;
+    unsigned long long* neartie;  // optional device counter the kernels ADD near-tie rows to (include/ctvq.h), may be null
 };
+
+// Absolute term of the tensor-core candidate window, in units of (|z|^2 + max|e|^2): 2^-20 covers the fp32 rounding of
+// the accumulation and of the distance formula itself; the extra 1e-6 widens the window by >= CTVQ_NEAR_TIE_REL * d1
+// (d1 <= 2 (|z|^2 + max|e|^2)), so the exact SECOND-best code of every near-tie row is among the survivors as well and
+// the near-tie count falls out of the exact re-scoring loop.
+constexpr float kWinAbs = 9.5367431640625e-7f + 1.0e-6f;
+
+// near-tie predicate on the exact fp32 distances d1 <= d2 of the best and second-best code (d2 = +inf: single code)
+__device__ __forceinline__ bool near_tie(float d1, float d2) {
+    return __fsub_rn(d2, d1) <= __fmul_rn(CTVQ_NEAR_TIE_REL, fabsf(d1));  // '<=': an exact tie at distance 0 counts too
+}
 
 struct Workspace {  // layout of the caller-provided zero-initialised buffer
     double loss_acc[CTVQ_MAX_CODEBOOKS];

@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(256) vq_fwd_simt_kernel(const QuantParams p) {
     }
 
     const int tk = tid & 15, tm = tid >> 4;
-    float bestv[RM];
+    float bestv[RM], secv[RM];  // running best / second-best distance (the latter only feeds the near-tie count)
     int besti[RM];
 #pragma unroll
-    for (int r = 0; r < RM; ++r) { bestv[r] = CUDART_INF_F; besti[r] = 0; }
+    for (int r = 0; r < RM; ++r) { bestv[r] = CUDART_INF_F; secv[r] = CUDART_INF_F; besti[r] = 0; }
 
     const bool e_vec = ((reinterpret_cast<uintptr_t>(E) & 15) == 0) && ((d & 3) == 0);
     const int ktiles = (K + kTK - 1) / kTK;
@@ -180,30 +180,38 @@ __global__ void __launch_bounds__(256) vq_fwd_simt_kernel(const QuantParams p) {
         for (int r = 0; r < RM; ++r) {
             const int m = (RM == 8) ? tm * 4 + (r & 3) + (r >> 2) * (TM / 2) : tm * 4 + r;
             const float zz = zz_s[m];
-            float bv = CUDART_INF_F;
+            float bv = CUDART_INF_F, sv = CUDART_INF_F;
             int bi = 0x7fffffff;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int k = kt * kTK + tk + 16 * i;
                 const float dist = dist_f32(zz, ee_s[tk + 16 * i], acc[r][i]);
-                const bool take = (k < K) && !(dist >= bv) && (bv == bv);
-                if (take) { bv = dist; bi = k; }
+                const bool take = (k < K) && (bi == 0x7fffffff || (!(dist >= bv) && (bv == bv)));  // the first code seeds the scan (all-+inf row -> lowest k)
+                if (take) { sv = bv; bv = dist; bi = k; }  // the old best (<= old second) becomes the second
+                else if (k < K) sv = fminf(sv, dist);
             }
+            // merging two disjoint sets: second = min(second_a, second_b, max(best_a, best_b))
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const float os = __shfl_xor_sync(0xffffffffu, sv, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                sv = fminf(fminf(sv, os), fmaxf(bv, ov));
                 if (lex_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
             }
-            if (lex_better(bv, bi, bestv[r], besti[r])) { bestv[r] = bv; besti[r] = bi; }
+            secv[r] = fminf(fminf(secv[r], sv), kt == 0 ? CUDART_INF_F : fmaxf(bestv[r], bv));
+            if (kt == 0 || lex_better(bv, bi, bestv[r], besti[r])) { bestv[r] = bv; besti[r] = bi; }
         }
     }
     if (tk == 0) {
+        unsigned nnear = 0u;
 #pragma unroll
         for (int r = 0; r < RM; ++r) {
             const int m = (RM == 8) ? tm * 4 + (r & 3) + (r >> 2) * (TM / 2) : tm * 4 + r;
             idx_s[m] = besti[r];
+            if (row0 + m < p.N && bestv[r] == bestv[r]) nnear += near_tie(bestv[r], secv[r]) ? 1u : 0u;
         }
+        if (p.neartie && nnear) atomicAdd(p.neartie, (unsigned long long)nnear);  // rare: <~1 % of the rows
     }
     __syncthreads();
     if (tid < TM && lvalid) p.idx[seg][((size_t)lb * p.C + c) * HW + lp] = (long long)idx_s[tid];

@@ -86,13 +86,15 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
     tc_fence_after();
     if (tid < C) {
         float mx = 0.0f;
-        for (int k = 0; k < K; ++k) mx = fmaxf(mx, ee_s[tid * Kpad + k]);
-        emax_s[tid] = sqrtf(mx) * 1.0001f;
+        bool poisoned = false;  // fmaxf drops NaN: a NaN code norm must poison the bound (the row then takes the exact scan)
+        for (int k = 0; k < K; ++k) { const float v = ee_s[tid * Kpad + k]; poisoned |= (v != v); mx = fmaxf(mx, v); }
+        emax_s[tid] = poisoned ? CUDART_NAN_F : sqrtf(mx) * 1.0001f;
     }
     const uint32_t tmem_base = *tmem_slot;
     __syncthreads();
 
     uint32_t phase_a = 0, phase_m = 0;
+    unsigned nnear = 0u;  // near-tie rows seen by this thread (include/ctvq.h)
     for (int c = 0; c < C; ++c) lsum_s[c * kThreads + tid] = 0.0f;
 
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
         phase_a ^= 1;
 
         // exact running best across the column chunks of one codebook (only used when a codebook spans > 256 codes)
-        float run_mn = CUDART_INF_F, run_bv = CUDART_INF_F;
+        float run_mn = CUDART_INF_F, run_bv = CUDART_INF_F, run_bv2 = CUDART_INF_F;  // exact best / second-best distance
         int run_bi = 0x7fffffff;
         bool run_bad = false;
         for (int u0 = 0; u0 < P.units;) {
@@ -180,8 +182,8 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
                 }
                 // rigorous bound on |tf32 distance - exact-chain distance|: operands truncated to 11 bits
                 const float emax = emax_s[c];
-                const float thr = 2.0f * (0.00390625f * sqrtf(zz) * 1.0001f * emax + 9.5367431640625e-7f * (zz + emax * emax));
-                if (ch == 0) { run_mn = CUDART_INF_F; run_bv = CUDART_INF_F; run_bi = 0x7fffffff; run_bad = false; }
+                const float thr = 2.0f * (0.00390625f * sqrtf(zz) * 1.0001f * emax + kWinAbs * (zz + emax * emax));
+                if (ch == 0) { run_mn = CUDART_INF_F; run_bv = CUDART_INF_F; run_bv2 = CUDART_INF_F; run_bi = 0x7fffffff; run_bad = false; }
                 run_mn = fminf(run_mn, mn);
                 const float lim = run_mn + thr;  // running minimum: a superset of the final survivor set
                 // pass 2: survivors
@@ -230,10 +232,12 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
                                         dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j + 3)), e4.w, dot);
                                     }
                                     const float dist = dist_f32(zz, ee_s[c * Kpad + k], dot);
-                                    if (dist < run_bv) { run_bv = dist; run_bi = k; }  // ascending k: strict '<' keeps the first minimum
+                                    if (dist < run_bv) { run_bv2 = run_bv; run_bv = dist; run_bi = k; }  // ascending k: strict '<' keeps the first minimum
+                                    else run_bv2 = fminf(run_bv2, dist);
                                 }
                             }
                         }
+                        if (last && !run_bad && run_bi != 0x7fffffff) nnear += near_tie(run_bv, run_bv2) ? 1u : 0u;
                         if (last && (run_bad || run_bi == 0x7fffffff)) {
                             // non-finite row: exact scan of every code with torch.argmin's NaN rule
                             run_bv = CUDART_INF_F; run_bi = 0x7fffffff;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
                                     dot = fmaf(*reinterpret_cast<const float*>(zrow + a_off(lane, j)),
                                                *reinterpret_cast<const float*>(ecb + e_off(k, j, Kpad)), dot);
                                 const float dist = dist_f32(zz, ee_s[c * Kpad + k], dot);
-                                if (!(dist >= run_bv) && (run_bv == run_bv)) { run_bv = dist; run_bi = k; }
+                                if (k == 0 || (!(dist >= run_bv) && (run_bv == run_bv))) { run_bv = dist; run_bi = k; }  // k == 0 seeds the scan (all-+inf row -> 0)
                             }
                         }
                         bv = run_bv; bi = run_bi;
@@ -276,6 +280,10 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
             __syncthreads();  // TMEM columns and (after the last round) the A slabs are free again
             u0 = u1;
         }
+    }
+    if (p.neartie) {
+        const unsigned tot = __reduce_add_sync(0xffffffffu, nnear);
+        if (lane == 0 && tot) atomicAdd(p.neartie, (unsigned long long)tot);
     }
     // ---- loss: per-codebook block sums -> fp64 atomics -> last CTA finalises -------------------------------------
     if (p.fused) {

@@ -119,10 +119,12 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
     tc_fence_after();
     if (warp == 0) {  // max |e_k|^2 over the real codes
         float mx = 0.0f;
-        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, ee_s[k]);
+        bool poisoned = false;  // fmaxf drops NaN: a NaN code norm must poison the bound (rows then take the exact scan)
+        for (int k = lane; k < K; k += 32) { const float v = ee_s[k]; poisoned |= (v != v); mx = fmaxf(mx, v); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) emax_s[0] = sqrtf(mx) * 1.0001f;
+        poisoned = __any_sync(0xffffffffu, poisoned);
+        if (lane == 0) emax_s[0] = poisoned ? CUDART_NAN_F : sqrtf(mx) * 1.0001f;
     }
     const uint32_t tmem_base = *tmem_slot;
     __syncthreads();
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
 
     uint32_t phase_m = 0;
     float lsum = 0.0f;
+    unsigned nnear = 0u;  // near-tie rows seen by this thread (include/ctvq.h)
 
     for (int it = 0; it < niter; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
         const int mtiles = (row0 + 128 < p.N) ? 2 : 1;
 
         float zz = 0.0f;
-        float run_mn = CUDART_INF_F, run_bv = CUDART_INF_F;
+        float run_mn = CUDART_INF_F, run_bv = CUDART_INF_F, run_bv2 = CUDART_INF_F;  // exact best / second-best distance
         int run_bi = 0x7fffffff;
         bool run_bad = false;
 #pragma unroll 1
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
                 }
                 const float mn = fminf(fminf(m0, m1), fminf(m2, m3));
                 run_mn = fminf(run_mn, mn);
-                const float thr = 2.0f * (2.0f * 2.05e-3f * sqrtf(zz) * 1.0001f * emax + 9.5367431640625e-7f * (zz + emax * emax));
+                const float thr = 2.0f * (2.0f * 2.05e-3f * sqrtf(zz) * 1.0001f * emax + kWinAbs * (zz + emax * emax));
                 const float lim = run_mn + thr;  // running minimum: a superset of the final survivor set
                 unsigned mask[NCH * 2];
                 int cnt = 0;
@@ -250,7 +253,8 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
                                 dot = fmaf(*reinterpret_cast<const float*>(zrow + (j + 3) * 128 + zsw[(j + 3) & 3]), e4.w, dot);
                             }
                             const float dist = dist_f32(zz, ee_s[k], dot);
-                            if (dist < run_bv) { run_bv = dist; run_bi = k; }  // ascending k: strict '<' keeps the first minimum
+                            if (dist < run_bv) { run_bv2 = run_bv; run_bv = dist; run_bi = k; }  // ascending k: strict '<' keeps the first minimum
+                            else run_bv2 = fminf(run_bv2, dist);
                         }
                     }
                 }
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
             }
         }
         if (valid) {
+            if (!run_bad && run_bi != 0x7fffffff) nnear += near_tie(run_bv, run_bv2) ? 1u : 0u;
             if (run_bad || run_bi == 0x7fffffff) {
                 // non-finite row: exact scan of every code with torch.argmin's NaN rule
                 run_bv = CUDART_INF_F; run_bi = 0x7fffffff;
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
                         dot = fmaf(*reinterpret_cast<const float*>(zrow + j * 128 + zsw[j & 3]),
                                    *reinterpret_cast<const float*>(erow + (j >> 5) * NK * 128 + (((((j & 31) >> 2) ^ (k & 7)) & 7) << 4) + ((j & 3) << 2)), dot);
                     const float dist = dist_f32(zz, ee_s[k], dot);
-                    if (!(dist >= run_bv) && (run_bv == run_bv)) { run_bv = dist; run_bi = k; }
+                    if (k == 0 || (!(dist >= run_bv) && (run_bv == run_bv))) { run_bv = dist; run_bi = k; }  // k == 0 seeds the scan (all-+inf row -> 0)
                 }
             }
             const int bi = run_bi;
@@ -303,6 +308,10 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
         }
         tc_fence_before();
         __syncthreads();  // TMEM columns and this ring slot are free again
+    }
+    if (p.neartie) {
+        const unsigned tot = __reduce_add_sync(0xffffffffu, nnear);
+        if (lane == 0 && tot) atomicAdd(p.neartie, (unsigned long long)tot);
     }
     if (p.fused) {
         double v = (double)lsum;

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     float lsum[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) lsum[i] = 0.0f;
+    unsigned nnear = 0u;  // near-tie rows seen by this thread (include/ctvq.h, CTVQ_NEAR_TIE_REL)
     if (warp == 4 * NWG) {
         // =============================== producer: TMA ring + MMA groups ===========================================
         if (lane == 0) {
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
                 // rigorous bound on |tf32 distance - exact-chain distance|: both operands lose at most
                 // 2^-10 relative (truncation to 10 mantissa bits) -> |dot error| <= (2^-9 + slack) |z||e|; scores are
                 // distances / -2, so the window is half the distance bound
-                const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx(zzc) * 1.0001f * emax + 9.5367431640625e-7f * (zzc + emax * emax));
+                const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx(zzc) * 1.0001f * emax + kWinAbs * (zzc + emax * emax));
                 const float lim = mx - 0.5f * thr;
                 // ---- pass 2: survivors as a bitmask (four independent accumulators per half); the upper half is still in
                 // registers from pass 1, only the lower half is re-read from TMEM
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
                 if (finite && cnt == 1) {
                     bi = mask0 ? __ffs(mask0) - 1 : 32 + __ffs(mask1) - 1;
                 } else {
-                    float bv = CUDART_INF_F;
+                    float bv = CUDART_INF_F, bv2 = CUDART_INF_F;  // exact best / second-best distance
                     bi = 0x7fffffff;
                     if (!finite) {
                         // non-finite row: exact scan of every code with torch.argmin's NaN rule
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
                                 dot = fmaf(zr[j], *reinterpret_cast<const float*>(erow + (j >> 5) * NK * 128 +
                                                                                    (((((j & 31) >> 2) ^ (k & 7)) & 7) << 4) + ((j & 3) << 2)), dot);
                             const float dist = dist_f32(zzc, ee[k], dot);
-                            if (!(dist >= bv) && (bv == bv)) { bv = dist; bi = k; }
+                            if (k == 0 || (!(dist >= bv) && (bv == bv))) { bv = dist; bi = k; }  // k == 0 seeds the scan: an all-+inf row answers 0 like torch.argmin
                         }
                     } else {
                         // exact re-scoring of the survivors, ascending k over the whole 64-bit mask (one loop: the trip count is
@@ -350,9 +351,14 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
                                 da = fmaf(zr[j + 3], a4.w, da); db = fmaf(zr[j + 3], b4.w, db);
                             }
                             const float dista = dist_f32(zzc, ee[ka], da), distb = dist_f32(zzc, ee[kb], db);
-                            if (dista < bv) { bv = dista; bi = ka; }  // ascending k: strict '<' keeps the first minimum
-                            if (distb < bv) { bv = distb; bi = kb; }  // (kb == ka when the mask ran out: no-op)
+                            if (dista < bv) { bv2 = bv; bv = dista; bi = ka; }  // ascending k: strict '<' keeps the first minimum
+                            else bv2 = fminf(bv2, dista);
+                            if (kb != ka) {  // (kb == ka when the mask ran out)
+                                if (distb < bv) { bv2 = bv; bv = distb; bi = kb; }
+                                else bv2 = fminf(bv2, distb);
+                            }
                         }
+                        nnear += near_tie(bv, bv2) ? 1u : 0u;  // the window holds the exact runner-up of every near-tie row (kWinAbs)
                     }
                 }
                 p.idx[seg][((size_t)b * C + c) * HWT + hw] = (long long)bi;
@@ -382,6 +388,10 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
         }
     }
     if (tid == 0) stamp(P, 5);  // this warp's last unit done
+    if (p.neartie && warp < 4 * NWG) {
+        const unsigned tot = __reduce_add_sync(0xffffffffu, nnear);
+        if (lane == 0 && tot) atomicAdd(p.neartie, (unsigned long long)tot);
+    }
     // ---- loss: warp sums -> fp64 atomics -> last CTA finalises -----------------------------------------------------
     if (p.fused) {
         if (warp < 4 * NWG) {

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
     const int nsup = (P.nsuper - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // super-tiles of this CTA
     const int NXG = (NU + 3) >> 2;
     float lsum = 0.0f;
+    unsigned nnear = 0u;  // near-tie rows seen by this thread (include/ctvq.h)
 
     if (warp == 4 * T + 2) {
         // ===================================== TMA-A lane: super-tile slabs ==========================================
@@ -257,14 +258,14 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                 return ZREG ? zr[ZREG ? j : 0] : *reinterpret_cast<const float*>(zrow + j * 128 + zsw[j & 3]);
             };
             // rigorous bound on |tf32 distance - exact-chain distance|; scores are distances / -2
-            const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx_s(zz) * 1.0001f * emax + 9.5367431640625e-7f * (zz + emax * emax));
+            const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx_s(zz) * 1.0001f * emax + kWinAbs * (zz + emax * emax));
             // Running state.  Exact distances are only needed to COMPARE candidates, and an L2 round trip per unit would stall
             // the few warps an SM has, so survivors are QUEUED (three register slots: code + an upper bound of its
             // approximate score = the running maximum when it was queued, hence non-decreasing along the queue).  A later
             // unit that lifts the window above the oldest bounds drops them unscored -- the usual fate of every provisional
             // maximum -- and what is left at the end of the row is scored in one go, two chains interleaved; a row whose
             // final window holds a single code never computes an exact distance.  Queue overflow settles it exactly.
-            float run_mx = -CUDART_INF_F, run_bv = CUDART_INF_F, ex_ub = -CUDART_INF_F;
+            float run_mx = -CUDART_INF_F, run_bv = CUDART_INF_F, run_bv2 = CUDART_INF_F, ex_ub = -CUDART_INF_F;
             float qu0 = 0.0f, qu1 = 0.0f, qu2 = 0.0f;
             int run_bi = 0x7fffffff, qk0 = -1, qk1 = -1, qk2 = -1, qn = 0;
             bool bad = !(zz < CUDART_INF_F);
@@ -280,7 +281,8 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                     dot = fmaf(zat(j + 3), e4.w, dot);
                 }
                 const float dist = dist_f32(zz, __ldg(P.ee + k), dot);
-                if (dist < run_bv) { run_bv = dist; run_bi = k; }  // strict '<' keeps the first minimum
+                if (dist < run_bv) { run_bv2 = run_bv; run_bv = dist; run_bi = k; }  // strict '<' keeps the first minimum
+                else run_bv2 = fminf(run_bv2, dist);
             };
             auto score2 = [&](int ka, int kb) {  // two codes (ka < kb, kb may be -1): both rows in flight, chains interleaved
                 const float4* ra = reinterpret_cast<const float4*>(E + (size_t)ka * D);
@@ -297,10 +299,12 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                     da = fmaf(z3, a4.w, da); db = fmaf(z3, b4.w, db);
                 }
                 const float dista = dist_f32(zz, __ldg(P.ee + ka), da);
-                if (dista < run_bv) { run_bv = dista; run_bi = ka; }
+                if (dista < run_bv) { run_bv2 = run_bv; run_bv = dista; run_bi = ka; }
+                else run_bv2 = fminf(run_bv2, dista);
                 if (kb >= 0) {
                     const float distb = dist_f32(zz, __ldg(P.ee + kb), db);
-                    if (distb < run_bv) { run_bv = distb; run_bi = kb; }
+                    if (distb < run_bv) { run_bv2 = run_bv; run_bv = distb; run_bi = kb; }
+                    else run_bv2 = fminf(run_bv2, distb);
                 }
             };
 #pragma unroll 1
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                         if (drop == 1) { qk0 = qk1; qu0 = qu1; qk1 = qk2; qu1 = qu2; }
                         else if (drop == 2) { qk0 = qk2; qu0 = qu2; }
                         qn -= drop;
-                        if (run_bi != 0x7fffffff && ex_ub < lim) { run_bi = 0x7fffffff; run_bv = CUDART_INF_F; }
+                        if (run_bi != 0x7fffffff && ex_ub < lim) { run_bi = 0x7fffffff; run_bv = CUDART_INF_F; run_bv2 = CUDART_INF_F; }
                         while (mk) {
                             const int k = kc * 64 + __ffsll((long long)mk) - 1;
                             mk &= mk - 1;
@@ -378,6 +382,7 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                     if (qn == 3) score(qk2);
                 }
             }
+            if (valid && !bad && run_bi != 0x7fffffff) nnear += near_tie(run_bv, run_bv2) ? 1u : 0u;
             if (valid) {
                 if (bad || run_bi == 0x7fffffff) {
                     // non-finite row: exact scan of every code with torch.argmin's NaN rule
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
 #pragma unroll(ZREG ? D : 8)
                         for (int j = 0; j < D; ++j) dot = fmaf(zat(j), __ldg(erow + j), dot);
                         const float dist = dist_f32(zz, __ldg(P.ee + k), dot);
-                        if (!(dist >= run_bv) && (run_bv == run_bv)) { run_bv = dist; run_bi = k; }
+                        if (k == 0 || (!(dist >= run_bv) && (run_bv == run_bv))) { run_bv = dist; run_bi = k; }  // k == 0 seeds the scan (all-+inf row -> 0)
                     }
                 }
                 const int bi = run_bi;
@@ -418,6 +423,10 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                 if (lane == 0) mbar_arrive(bar_aempty + 8 * ab);  // done reading the slab
             }
         }
+    }
+    if (p.neartie && warp < 4 * T) {
+        const unsigned tot = __reduce_add_sync(0xffffffffu, nnear);
+        if (lane == 0 && tot) atomicAdd(p.neartie, (unsigned long long)tot);
     }
     // ---- loss: warp sums -> fp64 atomics -> last CTA finalises -----------------------------------------------------
     if (p.fused) {

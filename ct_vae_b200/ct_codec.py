@@ -39,6 +39,7 @@ def ct_preprocess(x: Tensor, latents_shape: Sequence[int], num_embeddings: int, 
     rc = _lib.lib().ctvq_onehot_from_inds(idx.data_ptr(), b, s, num_embeddings, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                           dev.index, sp)
     _lib.check(rc, "ctvq_onehot_from_inds")
+    _lib.maybe_validate(ws, dev, sp, "ct_preprocess")  # CTVQ_VALIDATE / set_validate(True): raise like F.one_hot does
     return out
 
 

@@ -35,8 +35,24 @@ def _bf16_operands(z: Tensor, es: Sequence[Tensor]):
     return z.float(), [e.to(torch.bfloat16).float() for e in es]
 
 
-def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], chan_stride: int = 1) -> List[Tensor]:
+def _counter_ptr(counter: Optional[Tensor], dev) -> Optional[int]:
+    if counter is None:
+        return None
+    if counter.dtype != torch.int64 or counter.numel() != 1 or counter.device != dev:
+        raise RuntimeError("near-tie counter must be ONE int64 element on the latents' device")
+    return counter.data_ptr()
+
+
+def new_near_tie_counter(device) -> Tensor:
+    """Zero-initialised device counter the kernels ADD near-tie rows to (include/ctvq.h, CTVQ_NEAR_TIE_REL)."""
+    return torch.zeros(1, dtype=torch.int64, device=device)
+
+
+def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], chan_stride: int = 1,
+                 counter: Optional[Tensor] = None) -> List[Tensor]:
     """argmin indices [B, C, H, W] int64 for each input tensor, ONE launch for up to 4 same-shape inputs.
+    ``counter`` (one int64 on the device) accumulates the number of near-tie rows (north_star: relative top-2 gap
+    below 1e-6, counted and reported).
 
     Replaces models/mcq_vae.py:26-39 / :100-110 (and the x / y pair of models/ct_mcq_vae.py:530,536)."""
     _lib.require_cuda(*latents_list, *codebooks)
@@ -59,7 +75,8 @@ def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], ch
     sp = _lib.stream_ptr(dev)
     ws = _lib.workspace(dev, sp, c, k, d)
     rc = _lib.lib().ctvq_argmin(_lib.ptr_array(zs), len(zs), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride,
-                                _lib.F32, _lib.ptr_array(outs), ws.data_ptr(), ws.numel(), dev.index, sp)
+                                _lib.F32, _lib.ptr_array(outs), _counter_ptr(counter, dev), ws.data_ptr(), ws.numel(),
+                                dev.index, sp)
     _lib.check(rc, "ctvq_argmin")
     return outs
 
@@ -68,7 +85,8 @@ class _Quantize(torch.autograd.Function):
     """(latents, codebooks[, indices]) -> (straight-through output, summed vq_loss, indices, per-codebook losses)."""
 
     @staticmethod
-    def forward(ctx, latents: Tensor, beta: float, chan_stride: int, given_inds: Optional[Tensor], comm, *codebooks):
+    def forward(ctx, latents: Tensor, beta: float, chan_stride: int, given_inds: Optional[Tensor], comm, counter,
+                *codebooks):
         _lib.require_cuda(latents, *codebooks)
         z = latents.detach().contiguous()
         es = [e.detach() for e in codebooks]
@@ -76,13 +94,18 @@ class _Quantize(torch.autograd.Function):
         io_dtype = z.dtype
         dev = z.device
         if b == 0 or h * w == 0:
-            # empty batch: the reference returns an empty tensor and mse_loss(empty) = nan (models/vq_vae.py:47-50)
-            ctx.mark_non_differentiable()
+            # empty batch: the reference returns an empty tensor and mse_loss(empty) = nan (models/vq_vae.py:47-50); its
+            # codebook gradient is one_hot[0,K]^T @ g[0,d] = zeros, which this rank must still CONTRIBUTE to the
+            # all-reduce (a rank that skipped the collective would hang its peers)
             empty_inds = torch.empty((b, c, h, w), dtype=torch.int64, device=dev)
             nan = torch.full((), float("nan"), device=dev)
             ctx.empty = True
-            return (torch.empty((b, c * d, h, w), dtype=io_dtype, device=dev), nan, empty_inds,
-                    torch.full((c,), float("nan"), device=dev))
+            ctx.meta = (float(beta), int(chan_stride), b, dtot, h, w, c, d, k, comm)
+            ctx.dev, ctx.io_dtype = dev, io_dtype
+            per = torch.full((c,), float("nan"), device=dev)
+            ctx.mark_non_differentiable(empty_inds, per)
+            ctx.set_materialize_grads(False)
+            return torch.empty((b, c * d, h, w), dtype=io_dtype, device=dev), nan, empty_inds, per
         ctx.empty = False
         if io_dtype == torch.bfloat16:
             z, es = _bf16_operands(z, es)
@@ -94,8 +117,8 @@ class _Quantize(torch.autograd.Function):
         if given_inds is None:
             inds = torch.empty((b, c, h, w), dtype=torch.int64, device=dev)
             rc = L.ctvq_forward(z.data_ptr(), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride, _lib.F32,
-                                float(beta), inds.data_ptr(), out.data_ptr(), losses.data_ptr(), ws.data_ptr(),
-                                ws.numel(), dev.index, sp)
+                                float(beta), inds.data_ptr(), out.data_ptr(), losses.data_ptr(),
+                                _counter_ptr(counter, dev), ws.data_ptr(), ws.numel(), dev.index, sp)
             _lib.check(rc, "ctvq_forward")
         else:
             _lib.require_cuda(given_inds)
@@ -106,6 +129,7 @@ class _Quantize(torch.autograd.Function):
                                        chan_stride, _lib.F32, float(beta), out.data_ptr(), losses.data_ptr(),
                                        ws.data_ptr(), ws.numel(), dev.index, sp)
             _lib.check(rc, "ctvq_gather_st_loss")
+            _lib.maybe_validate(ws, dev, sp, "compute_latents")
         ctx.save_for_backward(z, inds, *es)
         ctx.meta = (float(beta), int(chan_stride), b, dtot, h, w, c, d, k, comm)
         ctx.io_dtype = io_dtype
@@ -119,7 +143,16 @@ class _Quantize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out, g_loss, _g_inds, _g_per):
         if ctx.empty:
-            return (None,) * len(ctx.needs_input_grad)
+            beta, cs, b, dtot, h, w, c, d, k, comm = ctx.meta
+            dev = ctx.dev
+            if comm is not None and hasattr(comm, "grad_buffer"):
+                ge = comm.grad_buffer((c, k, d)).zero_()
+            else:
+                ge = torch.zeros((c, k, d), dtype=torch.float32, device=dev)
+            if comm is not None:
+                ge = comm.allreduce_(ge)
+            gz = torch.zeros((b, dtot, h, w), dtype=ctx.io_dtype, device=dev)
+            return (gz, None, None, None, None, None, *ge.unbind(0))
         z, inds, *es = ctx.saved_tensors
         beta, cs, b, dtot, h, w, c, d, k, comm = ctx.meta
         dev = z.device
@@ -141,16 +174,19 @@ class _Quantize(torch.autograd.Function):
                                       dtot, h * w, c, d, k, cs, _lib.F32, beta, gz.data_ptr(), ge.data_ptr(),
                                       ws.data_ptr(), ws.numel(), dev.index, sp)
         _lib.check(rc, "ctvq_backward")
+        _lib.maybe_validate(ws, dev, sp, "quantiser backward")
         if comm is not None:
             ge = comm.allreduce_(ge)  # the one collective of the path, on the backward kernel's stream
         if ctx.io_dtype == torch.bfloat16:
             gz = gz.to(torch.bfloat16)
-        return (gz, None, None, None, None, *ge.unbind(0))
+        return (gz, None, None, None, None, None, *ge.unbind(0))
 
 
 def quantize(latents: Tensor, codebooks: Sequence[Tensor], beta: float, chan_stride: int = 1,
-             inds: Optional[Tensor] = None, comm=None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+             inds: Optional[Tensor] = None, comm=None, counter: Optional[Tensor] = None
+             ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Fused forward (argmin + gather + loss + straight-through), or gather by the given ``inds``.
+    ``counter``: optional one-element int64 device tensor the kernel adds this call's near-tie rows to.
 
     Replaces models/vq_vae.py:24-55 and models/mcq_vae.py:41-64,112-137."""
-    return _Quantize.apply(latents, beta, chan_stride, inds, comm, *codebooks)
+    return _Quantize.apply(latents, beta, chan_stride, inds, comm, counter, *codebooks)

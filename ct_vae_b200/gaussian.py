@@ -69,41 +69,72 @@ def reparameterize(mu: Tensor, logvar: Tensor, eps: Optional[Tensor] = None) -> 
     return reparam_kld(mu, logvar, eps)[0]
 
 
-class FusedGaussianMixin:
-    """Mix into a VanillaVAE / BetaVAE-shaped model: ``reparameterize`` also produces the KL term, which
-    ``loss_function`` then consumes instead of recomputing it (same dict keys and weighting as
-    models/vanilla_vae.py:133-146 and models/beta_vae.py:131-152)."""
-
-    _fused_kld = None
-
-    def reparameterize(self, mu: Tensor, logvar: Tensor) -> Tensor:
-        z, kld = reparam_kld(mu, logvar)
-        self._fused_kld = (mu, logvar, kld)
-        return z
-
-    def _kld(self, mu: Tensor, log_var: Tensor) -> Tensor:
-        cached = self._fused_kld
-        if cached is not None and cached[0] is mu and cached[1] is log_var:
-            return cached[2]
-        return reparam_kld(mu, log_var, torch.zeros_like(mu))[1]
+# ----------------------------------------------------------------------------------------------------------------------
+# injection into the reference's VanillaVAE / BetaVAE
+# ----------------------------------------------------------------------------------------------------------------------
+def _fused_reparameterize(self, mu: Tensor, logvar: Tensor) -> Tensor:
+    """Replaces VanillaVAE.reparameterize (models/vanilla_vae.py:107-117) / BetaVAE.reparameterize
+    (models/beta_vae.py:112-122): same eps draw (randn_like on a tensor of logvar's shape/dtype/device), one kernel that
+    also leaves the KL term of loss_function behind, keyed by the identity of (mu, logvar)."""
+    z, kld = reparam_kld(mu, logvar)
+    self._ctvq_kld = (mu, logvar, kld)
+    return z
 
 
-def vanilla_loss(recons: Tensor, inp: Tensor, kld: Tensor, M_N: float) -> dict:
-    """models/vanilla_vae.py:139-146 given the fused KL term."""
+def _kld_of(self, mu: Tensor, log_var: Tensor) -> Tensor:
+    cached = getattr(self, "_ctvq_kld", None)
+    if cached is not None and cached[0] is mu and cached[1] is log_var:
+        self._ctvq_kld = None  # single use: the autograd graph of that forward is about to be consumed
+        return cached[2]
+    # loss_function called on tensors that did not come from this module's reparameterize: KL term alone
+    return reparam_kld(mu, log_var, torch.zeros_like(mu))[1]
+
+
+def _vanilla_loss_function(self, *args, **kwargs) -> dict:
+    """Replaces VanillaVAE.loss_function (models/vanilla_vae.py:128-146): same arguments, same dict."""
+    recons, inp, mu, log_var = args[0], args[1], args[2], args[3]
+    kld_weight = kwargs["M_N"]
     recons_loss = torch.nn.functional.mse_loss(recons, inp)
-    loss = recons_loss + M_N * kld
-    return {"loss": loss, "Reconstruction_Loss": recons_loss.detach(), "KLD": -kld.detach()}
+    kld_loss = _kld_of(self, mu, log_var)
+    loss = recons_loss + kld_weight * kld_loss
+    return {"loss": loss, "Reconstruction_Loss": recons_loss.detach(), "KLD": -kld_loss.detach()}
 
 
-def beta_loss(recons: Tensor, inp: Tensor, kld: Tensor, M_N: float, *, loss_type: str, beta: float, gamma: float,
-              C_max: float, C_stop_iter: float, num_iter: int) -> dict:
-    """models/beta_vae.py:139-152 given the fused KL term (``num_iter`` already incremented, :132)."""
+def _beta_loss_function(self, *args, **kwargs) -> dict:
+    """Replaces BetaVAE.loss_function (models/beta_vae.py:130-152): same arguments, same dict, same ``num_iter`` counter
+    and capacity schedule C = clamp(C_max / C_stop_iter * num_iter, 0, C_max) for loss type 'B'."""
+    self.num_iter += 1
+    recons, inp, mu, log_var = args[0], args[1], args[2], args[3]
+    kld_weight = kwargs["M_N"]
     recons_loss = torch.nn.functional.mse_loss(recons, inp)
-    if loss_type == "H":
-        loss = recons_loss + beta * M_N * kld
-    elif loss_type == "B":
-        C = min(max(C_max / C_stop_iter * num_iter, 0.0), C_max)
-        loss = recons_loss + gamma * M_N * (kld - C).abs()
+    kld_loss = _kld_of(self, mu, log_var)
+    if self.loss_type == "H":
+        loss = recons_loss + self.beta * kld_weight * kld_loss
+    elif self.loss_type == "B":
+        self.C_max = self.C_max.to(inp.device)
+        C = torch.clamp(self.C_max / self.C_stop_iter * self.num_iter, 0, self.C_max.data[0])
+        loss = recons_loss + self.gamma * kld_weight * (kld_loss - C).abs()
     else:
         raise ValueError("Undefined loss type.")
-    return {"loss": loss, "Reconstruction_Loss": recons_loss, "KLD": kld}
+    return {"loss": loss, "Reconstruction_Loss": recons_loss, "KLD": kld_loss}
+
+
+def install(*classes) -> int:
+    """Rebind ``reparameterize`` and ``loss_function`` of the given VanillaVAE / BetaVAE classes (or of the ``models``
+    package when called as ``install(models)``) to the fused kernel path.  A class is treated as Beta-shaped when it has
+    the ``num_iter`` counter of models/beta_vae.py:10.  Idempotent; returns the number of classes patched."""
+    todo = []
+    for c in classes:
+        if isinstance(c, type):
+            todo.append(c)
+        else:  # a package / module: pick the two classes by name
+            todo += [getattr(c, n) for n in ("VanillaVAE", "BetaVAE") if isinstance(getattr(c, n, None), type)]
+    n = 0
+    for cls in todo:
+        if cls.__dict__.get("_ctvq_fused_gaussian", False):
+            continue
+        cls.reparameterize = _fused_reparameterize
+        cls.loss_function = _beta_loss_function if hasattr(cls, "num_iter") else _vanilla_loss_function
+        cls._ctvq_fused_gaussian = True
+        n += 1
+    return n

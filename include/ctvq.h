@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CTVQ_VERSION 100          /* 0.1.0 */
+#define CTVQ_VERSION 200          /* 0.2.0: near-tie counter, error-flag read-back, bf16 */
 #define CTVQ_MAX_CODEBOOKS 64
 #define CTVQ_MAX_SEGMENTS 4
 
@@ -58,11 +58,26 @@ const char* ctvq_strerror(int rc);
  * rewritten each call).  Passing only ctvq_workspace_bytes(0,0,0) is valid: such calls take the other kernels. */
 size_t ctvq_workspace_bytes(int C, int K, int d);
 
+/* Index validation.  Every entry point that CONSUMES caller-supplied indices (ctvq_gather_st_loss, ctvq_backward,
+ * ctvq_onehot_from_inds) clamps an index outside [0, K) and sets bit 0 of an error word in the workspace header instead
+ * of faulting (the reference raises from scatter_ / F.one_hot, models/vq_vae.py:40, models/ct_mcq_vae.py:480).  This
+ * call copies the word to the host and clears it; it SYNCHRONISES `stream`.  *err_out != 0 -> the caller raises. */
+int ctvq_read_and_clear_err(void* workspace, size_t ws_bytes, unsigned* err_out_host, int device, void* stream);
+
 /* Force a kernel path for subsequent calls on this thread's library handle (tests/bench); AUTO picks
  * by shape.  Returns the previous value. */
 int ctvq_set_path(int path);
 /* Which path the last ctvq_argmin/ctvq_forward call on this host thread dispatched to. */
 int ctvq_last_path(void);
+
+/* NEAR-TIE ACCOUNTING (BASELINE.json north_star: "near-ties with a relative top-2 distance gap below 1e-6 are counted
+ * and reported, not hidden"; the distances are those of models/vq_vae.py:30-32, the winner that of :35).
+ * `neartie_count_out` (may be NULL) points to ONE device counter that ctvq_argmin / ctvq_forward ADD to: the number of
+ * (row, codebook) pairs whose best and second-best fp32 distances d1 <= d2 (arithmetic contract above) satisfy
+ * d2 - d1 <= 1e-6 * |d1| -- exact ties included, also at distance 0.  These are exactly the rows where a different summation order (the
+ * reference's sgemm) may legitimately pick the other code.  The caller zero-initialises the counter and may let it
+ * accumulate over many calls (no synchronisation here).  Rows with a non-finite distance are not counted. */
+#define CTVQ_NEAR_TIE_REL 1e-6f
 
 /* compute_inds — replaces VectorQuantizerMS.compute_inds (models/mcq_vae.py:26-39),
  * MultipleCodebookVectorQuantizer.compute_inds (:100-110) and the distance+argmin half of
@@ -71,7 +86,7 @@ int ctvq_last_path(void);
  * models/ct_mcq_vae.py:530,536,555-556); pass n_seg = 1 otherwise. */
 int ctvq_argmin(const void* const* z_segs, int n_seg, const void* const* codebooks, int64_t B, int Dtot,
                 int HW, int C, int d, int K, int chan_stride, int dtype, int64_t* const* idx_out_segs,
-                void* workspace, size_t ws_bytes, int device, void* stream);
+                unsigned long long* neartie_count_out, void* workspace, size_t ws_bytes, int device, void* stream);
 
 /* compute_latents — replaces VectorQuantizerMS.compute_latents (models/mcq_vae.py:41-64) and
  * MultipleCodebookVectorQuantizer.compute_latents (:112-127): gather by CALLER-SUPPLIED indices,
@@ -87,7 +102,8 @@ int ctvq_gather_st_loss(const void* z, const void* const* codebooks, const int64
  * loss + straight-through in one pass over z (the N x K distance matrix never reaches HBM). */
 int ctvq_forward(const void* z, const void* const* codebooks, int64_t B, int Dtot, int HW, int C, int d,
                  int K, int chan_stride, int dtype, float beta, int64_t* idx_out, void* q_out,
-                 float* loss_out, void* workspace, size_t ws_bytes, int device, void* stream);
+                 float* loss_out, unsigned long long* neartie_count_out, void* workspace, size_t ws_bytes,
+                 int device, void* stream);
 
 /* backward — replaces autograd through models/vq_vae.py:43-53:
  *   gz[b,ch,p] = sum over (c,j) with c*chan_stride+j == ch of

@@ -52,6 +52,14 @@ def argmin(latents: torch.Tensor, codebooks: Sequence[torch.Tensor], chan_stride
     return out
 
 
+def neartie_count(latents: torch.Tensor, codebooks: Sequence[torch.Tensor], chan_stride: int = 1) -> int:
+    """(row, codebook) pairs with a relative top-2 distance gap below 1e-6 (north_star), kernels' evaluation order."""
+    z, es, b, dtot, hw, c, d, k = _prep(latents, codebooks)
+    fn = lib().ctvq_c_neartie_count
+    fn.restype = ctypes.c_int64
+    return int(fn(_f(z), _ptrs(es), ctypes.c_int64(b), dtot, hw, c, d, k, chan_stride))
+
+
 def gather_st_loss(latents, inds, codebooks, beta: float, chan_stride: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
     z, es, b, dtot, hw, c, d, k = _prep(latents, codebooks)
     idx = inds.reshape(b, c, hw).contiguous()

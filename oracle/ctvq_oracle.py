@@ -177,7 +177,7 @@ def count_near_tie_rows(latents: Tensor, codebook: Tensor, rel: float = NEAR_TIE
         return 0
     top2 = torch.topk(dist, 2, dim=1, largest=False).values
     gap = (top2[:, 1] - top2[:, 0]).abs()
-    return int((gap < rel * top2[:, 0].abs()).sum())
+    return int((gap <= rel * top2[:, 0].abs()).sum())  # '<=': an exact tie at distance 0 counts too (include/ctvq.h)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -52,6 +52,40 @@ void ctvq_c_argmin(const float *z, const float *const *E, int64_t B, int Dtot, i
     free(ee);
 }
 
+/* Near-tie accounting (BASELINE.json north_star; include/ctvq.h CTVQ_NEAR_TIE_REL): number of (row, codebook) pairs
+ * whose best and second-best fp32 distances (models/vq_vae.py:30-32, evaluation order above) d1 <= d2 satisfy
+ * d2 - d1 <= 1e-6 * |d1| in fp32 arithmetic.  Rows with a non-finite distance are not counted. */
+int64_t ctvq_c_neartie_count(const float *z, const float *const *E, int64_t B, int Dtot, int HW, int C, int d, int K,
+                             int cs) {
+    float *ee = (float *)malloc(sizeof(float) * (size_t)K);
+    int64_t count = 0;
+    for (int c = 0; c < C; ++c) {
+        const float *Ec = E[c];
+        for (int k = 0; k < K; ++k) ee[k] = dot_seq(Ec + (long)k * d, 1, Ec + (long)k * d, 1, d);
+        for (int64_t b = 0; b < B; ++b)
+            for (int p = 0; p < HW; ++p) {
+                const float *zr = z + ((b * Dtot + (long)c * cs) * HW + p);
+                float zz = dot_seq(zr, HW, zr, HW, d);
+                float d1 = INFINITY, d2 = INFINITY;
+                int finite = 1;
+                for (int k = 0; k < K; ++k) {
+                    float dot = dot_seq(zr, HW, Ec + (long)k * d, 1, d);
+                    float dist = (zz + ee[k]) - 2.0f * dot;
+                    if (!isfinite(dist)) { finite = 0; break; }
+                    if (dist < d1) { d2 = d1; d1 = dist; }
+                    else if (dist < d2) d2 = dist;
+                }
+                if (finite && K >= 2) {
+                    volatile float gap = d2 - d1;
+                    volatile float lim = 1e-6f * fabsf(d1);
+                    if (gap <= lim) ++count;  /* '<=': an exact tie at distance 0 counts too */
+                }
+            }
+    }
+    free(ee);
+    return count;
+}
+
 /* models/vq_vae.py:43-55 (mcq_vae.py:45-64 per codebook, :117-125 slice/cat/sum) */
 void ctvq_c_gather_st_loss(const float *z, const float *const *E, const int64_t *idx, int64_t B, int Dtot, int HW,
                            int C, int d, int K, int cs, float beta, float *q_out, float *loss_out /* [C+1] */) {

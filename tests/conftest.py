@@ -68,7 +68,9 @@ class Golden:
         return float(self.t["beta"])
 
 
-QUANT_GOLDENS = [n for n in golden_names() if n not in ("reparam_kld", "vanilla_loss") and not n.startswith("ct_codec_")]
+QUANT_GOLDENS = [n for n in golden_names() if n not in ("reparam_kld", "vanilla_loss", "gaussian_losses")
+                 and not n.startswith(("ct_codec_", "nonfinite_"))]
+NONFINITE_GOLDENS = golden_names(["nonfinite_"])  # indices only: rows with NaN / inf / overflowing distances
 
 
 def rel_err(a, b):

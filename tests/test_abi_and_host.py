@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_error_strings():
     from ct_vae_b200 import _lib
     L = _lib.lib()
-    assert L.ctvq_version() == 100
+    assert L.ctvq_version() == 200
     assert b"unsupported" in L.ctvq_strerror(-2)
     assert b"bad argument" in L.ctvq_strerror(-1)
     assert L.ctvq_workspace_bytes(4, 64, 32) >= 64 * 8
@@ -43,7 +43,7 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     from ct_vae_b200 import _lib
     L = _lib.lib()
     # null pointers / bad sizes are refused before any CUDA call
-    assert L.ctvq_forward(None, None, 1, 4, 4, 1, 4, 8, 1, 0, 0.25, None, None, None, None, 0, 0, None) == -1
+    assert L.ctvq_forward(None, None, 1, 4, 4, 1, 4, 8, 1, 0, 0.25, None, None, None, None, None, 0, 0, None) == -1
     assert L.ctvq_reparam_kld_fwd(None, None, None, 1, 1, None, None, None, 0, 0, None) == -1
 
 

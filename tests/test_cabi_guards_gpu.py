@@ -60,11 +60,16 @@ def test_no_write_outside_the_output_buffers(shape):
         out_b, out = _guarded(n_out, torch.float32, dev, SENT_F)
         idx_b, idx = _guarded(n_idx, torch.int64, dev, SENT_I)
         loss_b, loss = _guarded(C + 1, torch.float32, dev, SENT_F)
+        cnt_b, cnt = _guarded(1, torch.int64, dev, SENT_I)
+        cnt.zero_()
         rc = L.ctvq_forward(z.data_ptr(), ptrs, B, Dtot, HW, C, d, K, cs, 0, 0.25, idx.data_ptr(), out.data_ptr(),
-                            loss.data_ptr(), ws.data_ptr(), ws.numel(), 0, sp)
+                            loss.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(), 0, sp)
         assert rc == 0, L.ctvq_strerror(rc)
         torch.cuda.synchronize()
         assert _intact(out_b, n_out, SENT_F) and _intact(idx_b, n_idx, SENT_I) and _intact(loss_b, C + 1, SENT_F)
+        assert _intact(cnt_b, 1, SENT_I)
+        # near-tie counter (include/ctvq.h): exact against the C oracle's count in the same evaluation order
+        assert int(cnt.item()) == CO.neartie_count(z.cpu(), [e.cpu() for e in books], cs)
         assert bool((out != SENT_F).all()) and bool((idx >= 0).all()) and bool((idx < K).all())
         ref = CO.argmin(z.cpu(), [e.cpu() for e in books], cs)
         assert torch.equal(idx.cpu().view(B, C, H, W), ref)
@@ -101,7 +106,7 @@ def test_error_convention_on_device():
     loss = torch.empty(2, device=dev)
     sp = torch.cuda.current_stream(dev).cuda_stream
     args = lambda dt, d, wsn: (z.data_ptr(), ptrs, 2, 8, 4, 1, d, 4, 1, dt, 0.25, idx.data_ptr(), out.data_ptr(),
-                               loss.data_ptr(), ws.data_ptr(), wsn, 0, sp)
+                               loss.data_ptr(), None, ws.data_ptr(), wsn, 0, sp)
     assert L.ctvq_forward(*args(0, 8, ws.numel())) == 0
     assert L.ctvq_forward(*args(1, 8, ws.numel())) == -2       # CTVQ_BF16 pointers: unsupported in this build
     assert L.ctvq_forward(*args(0, 9, ws.numel())) == -1       # slice exceeds the channel count

@@ -10,7 +10,7 @@ Tolerances (north_star): indices bit-exact outside counted near-ties; losses / o
 import pytest
 import torch
 
-from conftest import QUANT_GOLDENS, Golden, rel_err
+from conftest import NONFINITE_GOLDENS, QUANT_GOLDENS, Golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -96,6 +96,8 @@ def test_golden_forward_backward(env, name, path):
     if not external:
         c_inds = CO.argmin(g["z"], g.codebooks).reshape(inds.shape)
         assert torch.equal(inds.cpu(), c_inds), "indices differ from the C oracle (same evaluation order)"
+        # north_star: near-ties are counted and reported -- the kernel's counter equals the C oracle's count exactly
+        assert m.near_tie_rows() == CO.neartie_count(g["z"], g.codebooks), "near-tie counter differs from the C oracle"
     # (1) vs the reference: only counted near-ties may differ
     near = hard = 0
     zc = g["z"]
@@ -189,6 +191,8 @@ def test_seeded_vs_oracles(env, cfg, path):
     inds_cpu = inds.cpu().reshape(B, C, H, W)
     # C oracle: same evaluation order -> exact
     assert torch.equal(inds_cpu, CO.argmin(z_cpu, books_cpu)), "indices differ from the C oracle"
+    near_rows = m.near_tie_rows()
+    assert near_rows == CO.neartie_count(z_cpu, books_cpu), "near-tie counter differs from the C oracle"
     # torch oracle (= reference ATen arithmetic): near-ties only
     ref_inds = O.mcq_compute_inds(z_cpu, books_cpu)
     near = hard = 0
@@ -204,7 +208,9 @@ def test_seeded_vs_oracles(env, cfg, path):
     assert rel_err(z.grad.cpu(), gz) < TOL
     for e, ref in zip(books, ges):
         assert rel_err(e.grad.cpu(), ref) < TOL
-    print(f"{name}[{path}]: rows={B * H * W * C} near-tie mismatches vs reference arithmetic: {near}")
+    if kind == "init":  # the tie-heavy case (|z|^2 dominates the distance): every flip sits on a counted near-tie row
+        assert near <= near_rows, "an index that differs from the reference's must sit on a counted near-tie row"
+    print(f"{name}[{path}]: rows={B * H * W * C} near-tie rows counted: {near_rows}, index mismatches vs reference arithmetic: {near}")
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -307,6 +313,75 @@ def test_cuda_graph_capture_forward_backward(env):
     graph.replay()
     torch.cuda.synchronize()
     assert rel_err(loss.detach().cpu(), g["loss"]) < TOL, "workspace must be self-cleaning across replays"
+
+
+@pytest.mark.parametrize("path", ["simt", "tc", "auto"])
+@pytest.mark.parametrize("name", NONFINITE_GOLDENS)
+def test_non_finite_goldens(env, name, path):
+    """NaN / +-inf / overflowing latents in tcgen05-covered shapes, minted from the live reference
+    (tests/golden/make_golden_r2.py): rows with a non-finite distance follow torch.argmin (first NaN wins; an all-+inf
+    row answers 0); every row equals the C oracle."""
+    pkg, _lib, O, CO = env
+    g = Golden(name)
+    dev = torch.device("cuda:0")
+    books = g.codebooks
+    k, d = books[0].shape
+    if g.is_mcq:
+        m = pkg.MultipleCodebookVectorQuantizer(k, d * len(books), len(books), 0.25)
+        for q, e in zip(m.quantizers, books):
+            q.embedding.weight.data.copy_(e)
+    else:
+        m = pkg.VectorQuantizerMS(k, d, 0.25)
+        m.embedding.weight.data.copy_(books[0])
+    m = m.to(dev)
+    z = g["z"]
+    _select_path(_lib, path, m, z)
+    try:
+        inds = m.compute_inds(z.to(dev))
+        _, _, inds_fused = m(z.to(dev), inds=True)  # the fused launch must survive the same rows (no OOB gather)
+    except RuntimeError as e:
+        if path == "tc" and "unsupported" in str(e):
+            pytest.skip("shape not covered by the tcgen05 kernel")
+        raise
+    torch.cuda.synchronize()
+    ref = g["inds"].reshape(z.shape[0], len(books), z.shape[2], z.shape[3])
+    got = inds.cpu().reshape(ref.shape)
+    assert torch.equal(got, inds_fused.cpu().reshape(ref.shape))
+    assert int(got.min()) >= 0 and int(got.max()) < k
+    assert torch.equal(got, CO.argmin(z, books).reshape(ref.shape)), "kernel and C oracle disagree"
+    for c in range(len(books)):
+        zs = z[:, c:c + d]
+        bad = ~torch.isfinite(zs).all(dim=1) | (zs.abs() > 1e19).any(dim=1)
+        assert torch.equal(got[:, c][bad], ref[:, c][bad]), "non-finite rows must follow torch.argmin"
+
+
+def test_out_of_range_indices_raise_under_validation(env):
+    """The reference raises from scatter_ / F.one_hot on an index outside [0, K) (models/vq_vae.py:40,
+    models/ct_mcq_vae.py:480); the kernels clamp and flag, and the flag surfaces as IndexError either at an explicit
+    check point (raise_if_bad_indices) or after every call under set_validate(True) / CTVQ_VALIDATE=1."""
+    pkg, _lib, O, CO = env
+    dev = torch.device("cuda:0")
+    m = pkg.MultipleCodebookVectorQuantizer(8, 8, 2).to(dev)
+    z = torch.randn(2, 8, 3, 4, device=dev, requires_grad=True)
+    good = torch.randint(0, 8, (2, 2, 3, 4), device=dev)
+    pkg.raise_if_bad_indices()  # clean slate
+    for bad_value in (8, -1):
+        bad = good.clone()
+        bad[1, 1, 2, 3] = bad_value
+        out, loss = m.compute_latents(z, bad)  # not fatal: clamped
+        assert bool(torch.isfinite(out).all())
+        with pytest.raises(IndexError):
+            pkg.raise_if_bad_indices(dev)
+        pkg.raise_if_bad_indices(dev)  # cleared by the read
+        prev = pkg.set_validate(True)
+        try:
+            with pytest.raises(IndexError):
+                m.compute_latents(z, bad)
+            m.compute_latents(z, good)  # and valid indices pass
+            with pytest.raises(IndexError):
+                pkg.ct_codec.ct_preprocess(bad, (2, 8, 3, 4), 8, 2)
+        finally:
+            pkg.set_validate(prev)
 
 
 def test_bad_indices_are_flagged_not_fatal(env):

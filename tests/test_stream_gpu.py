@@ -50,6 +50,10 @@ def _module(pkg, K, D, kind, dev):
     ("d128_k1024", 8, 128, 16, 16, 1024, "trained"),
     ("d256_k300", 9, 256, 4, 8, 300, "init"),                 # 2.25 super-tiles of 128 rows
     ("d256_k2048", 2, 256, 16, 16, 2048, "trained"),
+    # the largest codebooks of BASELINE.json configs[3] (K = 16384), every row checked against the C oracle
+    ("d32_k16384", 8, 32, 16, 16, 16384, "trained"),          # 256 units, 4 super-tiles of 512 rows
+    ("d32_k16384_init", 4, 32, 16, 16, 16384, "init"),        # tie-heavy: |e| ~ 1/K, the window holds many codes
+    ("d256_k16384", 4, 256, 16, 16, 16384, "trained"),        # 8 super-tiles of 128 rows, 8 blocks per unit
 ])
 def test_stream_vs_oracles(env, cfg):
     pkg, _lib, O, CO = env
@@ -68,6 +72,7 @@ def test_stream_vs_oracles(env, cfg):
     inds_cpu = inds.cpu().reshape(B, 1, H, W)
     assert torch.equal(inds_cpu, CO.argmin(z_cpu, book)), "indices differ from the C oracle"
     assert torch.equal(only_inds.cpu().reshape(B, 1, H, W), inds_cpu), "argmin-only launch differs from the fused launch"
+    assert m.near_tie_rows() == 2 * CO.neartie_count(z_cpu, book), "near-tie counter (two launches) differs from the C oracle"
     ref_out, ref_loss, _ = O.mcq_compute_latents(z_cpu, inds_cpu, book, 0.25)
     assert torch.equal(out.cpu(), ref_out)
     assert rel_err(loss.cpu(), ref_loss) < TOL
