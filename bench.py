@@ -284,9 +284,10 @@ def main():
         collective = args.collective
         if collective == "peer":
             try:
-                # overlap: the all-reduce of step i runs on a side stream underneath the forward of step i+1 (its result is
-                # only needed by the optimizer); every timed region ends with comm.wait(), so all of them are inside it
-                comm = PeerGradComm(CFG["C"] * CFG["K"] * (CFG["D"] // CFG["C"]), dev, overlap=os.environ.get("CTVQ_PEER_OVERLAP", "1") != "0")
+                # fused: the backward kernel's last CTA runs the all-reduce (push over NVLink peer memory); everything is
+                # on ONE stream in program order -- the schedule a training step can actually use (the optimizer needs the
+                # reduced gradient before the next forward), nothing is hidden under the next step
+                comm = PeerGradComm(CFG["C"] * CFG["K"] * (CFG["D"] // CFG["C"]), dev)
             except Exception as e:  # no CUDA IPC / peer access on this box: NCCL carries the collective instead
                 print(f"[bench] peer collective unavailable ({e!r}); using NCCL", file=sys.stderr)
                 collective = "nccl"
@@ -378,6 +379,40 @@ def main():
     rows_per_gpu = B * H * W
     value = rows_per_gpu * world * args.steps / (ms * 1e-3)
 
+    # ---- collective check (outside the timed region): the reduced codebook gradient against the rank-ordered sum / world
+    collective_check = None
+    if world > 1:
+        def grads_with(c):
+            pkg.attach_grad_comm(m, c)
+            out, loss = m(z)
+            torch.autograd.backward([out, loss], [g_out, g_loss])
+            g = torch.stack([p.grad for p in params]).clone()
+            z.grad = None
+            for p in params:
+                p.grad = None
+            return g
+        g_red = grads_with(comm)
+        g_loc = grads_with(None)
+        pkg.attach_grad_comm(m, comm)
+        parts = [torch.empty_like(g_loc) for _ in range(world)]
+        dist.all_gather(parts, g_loc)
+        exp = torch.zeros_like(g_loc)
+        for part in parts:
+            exp = exp + part  # rank order, like the kernel
+        exp = exp * (1.0 / world)
+        reds = [torch.empty_like(g_red) for _ in range(world)]
+        dist.all_gather(reds, g_red)
+        identical = all(bool(torch.equal(reds[0], r_)) for r_ in reds[1:])
+        rel = float((g_red - exp).abs().max() / exp.abs().max().clamp_min(1e-30))
+        collective_check = {"collective": type(comm).__name__, "max_rel_err_vs_rank_ordered_sum": rel,
+                            "max_abs_err": float((g_red - exp).abs().max()), "identical_on_all_ranks": identical,
+                            "note": "expected value recomputed by a second local backward (fp32 atomics reorder the "
+                                    "local sums, hence a relative error instead of bit identity against it)"}
+        if hasattr(comm, "check"):
+            comm.check()
+        if rel > 1e-5 or (isinstance(comm, PeerGradComm) and not identical):
+            raise RuntimeError(f"collective check failed: {collective_check}")
+
     # ---- e2e: public API, latents from pinned host memory each step, loss read back --------------------
     e2e_steps = max(3, min(args.steps, 10))
     host_z = torch.randn(B, D, H, W).pin_memory()
@@ -445,8 +480,8 @@ def main():
                 "config": dict(workload_config(B, world), collective=(type(comm).__name__ if comm is not None else "none")),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * D * H * W * 4 * world,
                         "d2h_bytes_per_step": 4 * world, "steps": e2e_steps},
-                "gpu_launches": (2 + (1 if world > 1 else 0)) * args.steps,
-                "roofline": roofline, "kernels": kernels, "clocks": clocks, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "train": train}
+                "gpu_launches": (2 + (1 if world > 1 and not getattr(comm, "fuses_backward", False) else 0)) * args.steps,
+                "collective_check": collective_check, "roofline": roofline, "kernels": kernels, "clocks": clocks, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "train": train}
         emit(line)
     if world > 1:
         if comm is not None:

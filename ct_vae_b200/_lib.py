@@ -44,8 +44,9 @@ _SIGNATURES = {
     "ctvq_peer_export": (_i, [_vp, _vp, _i]),
     "ctvq_peer_import": (_i, [_vp, ctypes.POINTER(_vp), _i]),
     "ctvq_peer_close": (_i, [_vp, _i]),
-    "ctvq_peer_slot": (_vp, [_vp, _sz, ctypes.c_uint]),
-    "ctvq_peer_allreduce": (_i, [_vp, _i, _i, _sz, _sz, ctypes.c_uint, _f, _vp, _i, _vp]),
+    "ctvq_peer_allreduce": (_i, [_vp, _i, _i, _sz, _vp, _sz, ctypes.c_uint, _f, _vp, _vp, _sz, _i, _vp]),
+    "ctvq_backward_allreduce": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp,
+                                     _vp, _i, _i, _sz, ctypes.c_uint, _f, _vp, _vp, _sz, _i, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -25,6 +25,20 @@ struct DeviceGuard {
     }
 };
 
+}  // namespace ctvq
+namespace ctvq {
+int sm_count() {
+    static std::atomic<int> cache[64];  // per device ordinal; 0 = not queried yet
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 static int check_shape(int64_t B, int Dtot, int HW, int C, int d, int K, int cs, int dtype) {
     if (B <= 0 || Dtot <= 0 || HW <= 0 || C <= 0 || d <= 0 || K <= 0 || cs < 0) return CTVQ_E_BADARG;
     if (C > CTVQ_MAX_CODEBOOKS) return CTVQ_E_UNSUPPORTED;
@@ -181,10 +195,11 @@ int ctvq_forward(const void* z, const void* const* codebooks, int64_t B, int Dto
     return dispatch_forward(p, static_cast<cudaStream_t>(stream));
 }
 
-int ctvq_backward(const void* z, const void* const* codebooks, const int64_t* idx, const void* g_out,
-                  const float* g_loss, int64_t B, int Dtot, int HW, int C, int d, int K, int chan_stride, int dtype,
-                  float beta, void* gz_out, float* gE_out, void* workspace, size_t ws_bytes, int device,
-                  void* stream) {
+static int backward_impl(const void* z, const void* const* codebooks, const int64_t* idx, const void* g_out,
+                         const float* g_loss, int64_t B, int Dtot, int HW, int C, int d, int K, int chan_stride, int dtype,
+                         float beta, void* gz_out, float* gE_out, void* workspace, size_t ws_bytes, int device,
+                         void* stream, void* const* peer_bufs, int world, int rank, size_t count_max, unsigned epoch,
+                         float scale, float* gE_reduced_out) {
     if (!z || !idx || !g_loss || !gz_out || !gE_out || !codebooks || !workspace) return CTVQ_E_BADARG;
     if (ws_bytes < sizeof(Workspace)) return CTVQ_E_WORKSPACE;
     int rc = check_shape(B, Dtot, HW, C, d, K, chan_stride, dtype);
@@ -205,9 +220,33 @@ int ctvq_backward(const void* z, const void* const* codebooks, const int64_t* id
     p.B = B; p.N = B * (int64_t)HW;
     p.Dtot = Dtot; p.HW = HW; p.C = C; p.d = d; p.K = K; p.cs = chan_stride;
     p.beta = beta;
+    if (peer_bufs) {  // arm the fused collective: the last CTA of whichever backward kernel runs all-reduces gE_out
+        rc = make_peer_tail(p.peer, peer_bufs, world, rank, count_max, (size_t)C * K * d, epoch, scale, gE_reduced_out,
+                            static_cast<Workspace*>(workspace));
+        if (rc) return rc;
+    }
     DeviceGuard g(device);
     if (g.err != cudaSuccess) return (int)g.err;
     return launch_backward(p, static_cast<cudaStream_t>(stream));
+}
+
+int ctvq_backward(const void* z, const void* const* codebooks, const int64_t* idx, const void* g_out,
+                  const float* g_loss, int64_t B, int Dtot, int HW, int C, int d, int K, int chan_stride, int dtype,
+                  float beta, void* gz_out, float* gE_out, void* workspace, size_t ws_bytes, int device,
+                  void* stream) {
+    return backward_impl(z, codebooks, idx, g_out, g_loss, B, Dtot, HW, C, d, K, chan_stride, dtype, beta, gz_out, gE_out,
+                         workspace, ws_bytes, device, stream, nullptr, 0, 0, 0, 0u, 1.0f, nullptr);
+}
+
+int ctvq_backward_allreduce(const void* z, const void* const* codebooks, const int64_t* idx, const void* g_out,
+                            const float* g_loss, int64_t B, int Dtot, int HW, int C, int d, int K, int chan_stride,
+                            int dtype, float beta, void* gz_out, float* gE_local, void* const* peer_bufs, int world,
+                            int rank, size_t count_max, unsigned epoch, float scale, float* gE_reduced_out,
+                            void* workspace, size_t ws_bytes, int device, void* stream) {
+    if (!peer_bufs || !gE_reduced_out) return CTVQ_E_BADARG;
+    return backward_impl(z, codebooks, idx, g_out, g_loss, B, Dtot, HW, C, d, K, chan_stride, dtype, beta, gz_out, gE_local,
+                         workspace, ws_bytes, device, stream, peer_bufs, world, rank, count_max, epoch, scale,
+                         gE_reduced_out);
 }
 
 int ctvq_reparam_kld_fwd(const float* mu, const float* logvar, const float* eps, int64_t B, int L, float* z_out,
@@ -368,7 +407,7 @@ int ctvq_allreduce_codebook_grad(void* comm, float* gE, size_t count, float scal
     }
     if (scale != 1.0f) {
         size_t blocks = (count + 255) / 256;
-        if (blocks > 148 * 4) blocks = 148 * 4;
+        if (blocks > (size_t)sm_count() * 4) blocks = (size_t)sm_count() * 4;
         scale_kernel<<<(unsigned)blocks, 256, 0, s>>>(gE, count, scale);
         return (int)cudaGetLastError();
     }

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(kBT) vq_bwd_tile_kernel(const BwdParams p, con
         const float v = acc[i];
         if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
     }
+    peer_tail(p.peer, p.gE);  // fused collective (no-op unless ctvq_backward_allreduce armed it)
 }
 }  // namespace
 
@@ -175,7 +176,7 @@ int launch_backward_tiled(const BwdParams& p, cudaStream_t s) {
     const long long ntiles_ll = (p.N + TM - 1) / TM;
     if (ntiles_ll > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
     const int ntiles = (int)ntiles_ll;
-    int grid = 148 * per_sm;
+    int grid = sm_count() * per_sm;
     // small problems: do not pay one accumulator flush per idle CTA
     const int min_tiles_per_cta = 4;
     if ((long long)grid * min_tiles_per_cta > ntiles) grid = (ntiles + min_tiles_per_cta - 1) / min_tiles_per_cta;

@@ -144,13 +144,14 @@ __global__ void __launch_bounds__(2 * kHT) vq_bwd_c1_kernel(const BwdParams p, c
             if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
         }
     }
+    peer_tail(p.peer, p.gE);  // fused collective (no-op unless ctvq_backward_allreduce armed it)
 }
 
 template <int TM, bool GACC>
 int launch_c1(const BwdParams& p, size_t sm, int per_sm, int ntiles, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(vq_bwd_c1_kernel<TM, GACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;
-    int grid = 148 * per_sm;
+    int grid = sm_count() * per_sm;
     if (grid * 2 > ntiles) grid = (ntiles + 1) / 2;
     vq_bwd_c1_kernel<TM, GACC><<<grid, 2 * kHT, sm, s>>>(p, ntiles);
     return (int)cudaGetLastError();
@@ -184,7 +185,7 @@ int launch_backward_c1(const BwdParams& p, cudaStream_t s) {
     if (ntiles_ll > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
     if (!gacc) {
         // every CTA zeroes and flushes a [K,d] accumulator: only worth it when the rows outweigh that
-        const long long ctas = (ntiles_ll + 1) / 2 < 148LL * per_sm ? (ntiles_ll + 1) / 2 : 148LL * per_sm;
+        const long long ctas = (ntiles_ll + 1) / 2 < (long long)sm_count() * per_sm ? (ntiles_ll + 1) / 2 : (long long)sm_count() * per_sm;
         if ((double)p.N * p.d < 2.0 * (double)ctas * (double)kd) return CTVQ_E_UNSUPPORTED;
     } else if (p.N < 32768) {
         return CTVQ_E_UNSUPPORTED;  // tiny batches keep the direct kernel

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kBT, MINB) vq_bwd_fast_kernel(const BwdParams 
         const float v = acc[i];
         if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
     }
+    peer_tail(p.peer, p.gE);  // fused collective (no-op unless ctvq_backward_allreduce armed it)
 }
 
 template <int D, int C, int K, int HWT, int DTOT, int CS, int MINB>
@@ -202,7 +203,7 @@ int launch(const BwdParams& p, cudaStream_t s) {
     static_assert(smem <= (MINB == 2 ? 113 : 225) * 1024, "shared memory budget");
     const long long nt = (p.N + kTM - 1) / kTM;
     if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
-    int grid = 148 * MINB;
+    int grid = sm_count() * MINB;
     if (grid > nt) grid = (int)nt;
     if (grid < 1) grid = 1;
     auto kern = vq_bwd_fast_kernel<D, C, K, HWT, DTOT, CS, MINB>;
@@ -431,6 +432,7 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
         const float v = acc[i] + acc[CKD + i];
         if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
     }
+    peer_tail(p.peer, p.gE);  // fused collective: the last CTA pushes the finished gradient to every peer and reduces
 }
 
 template <int D, int C, int K, int HWT, int DTOT, int CS>
@@ -442,7 +444,7 @@ int launch_tma(const BwdParams& p, cudaStream_t s) {
     if (p.N % HWT != 0) return CTVQ_E_UNSUPPORTED;
     const long long nt = p.N / HWT;  // one image per tile
     if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
-    int grid = 148;
+    int grid = sm_count();
     if (grid > nt) grid = (int)nt;
     auto kern = vq_bwd_tma_kernel<D, C, K, HWT, DTOT, CS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -459,7 +461,7 @@ int launch_backward_fast(const BwdParams& p, cudaStream_t s) {
     // configs/mcq_vae.yaml: C=4, d=32, K=64, latents [B,128,8,8], overlapping slices
     if (p.d == 32 && p.C == 4 && p.K == 64 && p.HW == 64 && p.Dtot == 128 && p.cs == 1) {
         const bool go_ok = p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0;
-        if (go_ok && p.N >= 148 * 64 * 4 && !getenv("CTVQ_BWD_NO_TMA")) return launch_tma<32, 4, 64, 64, 128, 1>(p, s);
+        if (go_ok && p.N >= (long long)sm_count() * 64 * 4 && !getenv("CTVQ_BWD_NO_TMA")) return launch_tma<32, 4, 64, 64, 128, 1>(p, s);
         return launch<32, 4, 64, 64, 128, 1, 2>(p, s);
     }
     // configs/ct_mcq_vae.yaml: C=1, d=128, K=64, latents [B,128,8,8]

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "../../include/ctvq.h"
+#include "ctvq_peer.cuh"
 
 namespace ctvq {
 
@@ -75,7 +76,16 @@ struct BwdParams {
     int Dtot, HW, C, d, K, cs;
     float beta;
     int smem_acc;  // 1: privatise the [C,K,d] accumulator in shared memory
+    PeerTail peer; // world > 1: the last CTA all-reduces gE over NVLink peer memory (ctvq_backward_allreduce)
 };
+
+struct Workspace;
+// peer-tail descriptor from the caller's table of mapped symmetric buffers (ctvq_peer.cu); CTVQ_E_BADARG when inconsistent
+int make_peer_tail(PeerTail& t, void* const* peer_bufs, int world, int rank, size_t count_max, size_t count, unsigned epoch,
+                   float scale, float* out, Workspace* ws);
+
+// SMs of the CURRENT device (queried once per device, then cached): every persistent grid is sized from it
+int sm_count();
 
 // launch helpers implemented in the .cu files; return 0, a cudaError_t (>0) or a CTVQ_E_* (<0)
 int launch_forward_simt(const QuantParams& p, cudaStream_t s);
@@ -99,6 +109,8 @@ bool tc_supported(const QuantParams& p);
 int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s);  // shape-specialised tcgen05 kernels
 int launch_forward_tc_c1(const QuantParams& p, cudaStream_t s);    // single-codebook row-split tcgen05 kernels
 int launch_forward_tc_stream(const QuantParams& p, cudaStream_t s);  // single codebook of any size streamed through a TMA ring
+int launch_forward_tc_res(const QuantParams& p, cudaStream_t s);     // single codebook resident in shared memory (K <= 512 at D=64)
+bool res_supported(const QuantParams& p);
 bool stream_supported(const QuantParams& p);
 size_t stream_scratch_bytes(int K);  // scratch the streaming kernel needs behind the Workspace header
 constexpr size_t kScratchOffset = 1024;  // Workspace header rounded up

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) latent_ce_bwd_kernel(const float* __restr
 inline unsigned grid_for(long long items) {
     long long blocks = (items + 255) / 256;
     if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     return (unsigned)blocks;
 }
 }  // namespace

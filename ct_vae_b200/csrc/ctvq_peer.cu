@@ -1,7 +1,5 @@
-// One-shot all-reduce of the stacked codebook gradient over NVLink peer memory (declared in include/ctvq.h).
-// Replaces the NCCL call for the path's only collective when every rank sits on one NVSwitch box: the message is
-// 32 KB (latency-bound), so each rank simply reads all peers' slots through P2P-mapped pointers and sums them in
-// rank order after a flag handshake — one kernel, no second barrier (slots alternate by epoch parity).
+// Host side of the one-shot NVLink peer-memory all-reduce (protocol and device code: ctvq_peer.cuh): symmetric-buffer
+// management over CUDA IPC, the stand-alone collective kernel, and the fused backward + all-reduce entry point.
 #include <stdlib.h>
 #include <string.h>
 
@@ -9,62 +7,44 @@
 
 namespace ctvq {
 namespace {
-struct PeerParams {
-    const float* grad[CTVQ_MAX_PEERS];
-    unsigned int* flags[CTVQ_MAX_PEERS];
-    float* out;
-    size_t count;
-    int world, rank;
-    unsigned int epoch;
-    float scale;
-};
+__global__ void __launch_bounds__(512) peer_allreduce_kernel(const PeerTail t, const float* src) { peer_push_reduce(t, src); }
 
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+inline size_t flags_offset(size_t count_max, int world) { return (2 * (size_t)world * count_max * sizeof(float) + 255) & ~(size_t)255; }
 
-__global__ void __launch_bounds__(512) peer_allreduce_kernel(const PeerParams p) {
-    // (1) this rank's gradient slot is complete (stream order): tell every peer
-    if (blockIdx.x == 0 && threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.rank, p.epoch);
-    // (2) wait until every peer's slot of this epoch is complete (flags are monotonic, so every CTA may poll them)
-    if (threadIdx.x < p.world) {
-        const unsigned int* f = p.flags[p.rank] + threadIdx.x;
-        const long long t0 = clock64();
-        // back off between polls: in overlap mode this kernel shares its SMs with the next forward, whose persistent CTAs
-        // have a static share of the tiles -- a warp spinning at full rate on one scheduler slows the whole kernel
-        while ((int)(ld_acquire_sys(f) - p.epoch) < 0) {
-            __nanosleep(400);
-            if (clock64() - t0 > 6000000000LL) __trap();  // ~3 s: a missing peer traps instead of hanging the GPU
-        }
-    }
-    __syncthreads();
-    // (3) sum the slots in rank order: deterministic and bit-identical on every rank
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.count; i += (size_t)gridDim.x * blockDim.x) {
-        float s = 0.0f;
-#pragma unroll
-        for (int r = 0; r < CTVQ_MAX_PEERS; ++r)
-            if (r < p.world) s += __ldcv(p.grad[r] + i);
-        p.out[i] = s * p.scale;
-    }
+unsigned long long peer_timeout_ns() {  // wall-clock bound on the wait for a peer, CTVQ_PEER_TIMEOUT_MS (default 30 s)
+    static const unsigned long long ns = [] {
+        const char* e = getenv("CTVQ_PEER_TIMEOUT_MS");
+        const long long ms = e ? atoll(e) : 30000;
+        return (unsigned long long)(ms > 0 ? ms : 30000) * 1000000ull;
+    }();
+    return ns;
 }
-
-inline size_t flags_offset(size_t count_max) { return (2 * count_max * sizeof(float) + 255) & ~(size_t)255; }
 }  // namespace
+
+// Fills the tail descriptor from the caller's table of mapped peer buffers.  CTVQ_E_BADARG on inconsistent arguments.
+int make_peer_tail(PeerTail& t, void* const* peer_bufs, int world, int rank, size_t count_max, size_t count, unsigned epoch,
+                   float scale, float* out, Workspace* ws) {
+    if (!peer_bufs || !out || !ws || world < 1 || world > CTVQ_MAX_PEERS || rank < 0 || rank >= world || count == 0 ||
+        count > count_max || (count_max & 3))
+        return CTVQ_E_BADARG;
+    memset(&t, 0, sizeof(t));
+    for (int r = 0; r < world; ++r) {
+        if (!peer_bufs[r]) return CTVQ_E_BADARG;
+        t.recv[r] = static_cast<float*>(peer_bufs[r]);
+        t.flags[r] = reinterpret_cast<unsigned int*>(static_cast<char*>(peer_bufs[r]) + flags_offset(count_max, world));
+    }
+    t.out = out; t.ticket = &ws->ticket2; t.err = &ws->err;
+    t.count = count; t.count_max = count_max; t.timeout_ns = peer_timeout_ns();
+    t.world = world; t.rank = rank; t.epoch = epoch; t.scale = scale;
+    return CTVQ_OK;
+}
 }  // namespace ctvq
 
 using namespace ctvq;
 
 extern "C" {
 
-size_t ctvq_peer_buffer_bytes(size_t count_max, int world) {
-    (void)world;
-    return flags_offset(count_max) + 256;
-}
+size_t ctvq_peer_buffer_bytes(size_t count_max, int world) { return flags_offset(count_max, world < 1 ? 1 : world) + 256; }
 
 int ctvq_peer_alloc(void** dev_ptr_out, size_t count_max, int world, int device) {
     if (!dev_ptr_out || world < 1 || world > CTVQ_MAX_PEERS || count_max == 0) return CTVQ_E_BADARG;
@@ -113,43 +93,17 @@ int ctvq_peer_close(void* dev_ptr, int device) {
     return (int)cudaIpcCloseMemHandle(dev_ptr);
 }
 
-float* ctvq_peer_slot(void* own_buf, size_t count_max, unsigned epoch) {
-    return static_cast<float*>(own_buf) + (size_t)(epoch & 1u) * count_max;
-}
-
-int ctvq_peer_allreduce(void* const* peer_bufs, int world, int rank, size_t count_max, size_t count, unsigned epoch,
-                        float scale, float* out, int device, void* stream) {
-    if (!peer_bufs || !out || world < 1 || world > CTVQ_MAX_PEERS || rank < 0 || rank >= world || count == 0 ||
-        count > count_max)
-        return CTVQ_E_BADARG;
-    PeerParams p;
-    memset(&p, 0, sizeof(p));
-    for (int r = 0; r < world; ++r) {
-        if (!peer_bufs[r]) return CTVQ_E_BADARG;
-        p.grad[r] = static_cast<const float*>(peer_bufs[r]) + (size_t)(epoch & 1u) * count_max;
-        p.flags[r] = reinterpret_cast<unsigned int*>(static_cast<char*>(peer_bufs[r]) + flags_offset(count_max));
-    }
-    p.out = out; p.count = count; p.world = world; p.rank = rank; p.epoch = epoch; p.scale = scale;
+int ctvq_peer_allreduce(void* const* peer_bufs, int world, int rank, size_t count_max, const float* src, size_t count,
+                        unsigned epoch, float scale, float* out, void* workspace, size_t ws_bytes, int device, void* stream) {
+    if (!src || !workspace) return CTVQ_E_BADARG;
+    if (ws_bytes < sizeof(Workspace)) return CTVQ_E_WORKSPACE;
+    PeerTail t;
+    const int rc0 = make_peer_tail(t, peer_bufs, world, rank, count_max, count, epoch, scale, out, static_cast<Workspace*>(workspace));
+    if (rc0) return rc0;
     int prev = -1;
     cudaGetDevice(&prev);
     if (prev != device) cudaSetDevice(device);
-    // same shared-memory carve-out as the quantiser kernels (which take ~210 KB per SM): an SM configured for a small
-    // carve-out would have to drain and reconfigure before it can host the next forward's CTA, i.e. in overlap mode the
-    // forward would wait for this kernel's handshake on those SMs
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        cudaFuncSetAttribute(peer_allreduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
-    }
-    // SMALL CTAs: in overlap mode this kernel must co-reside with the next forward's 544-thread, 96-register CTA on the
-    // same SMs.  Measured at N=2: 512-thread CTAs delay the forward by 9 us (0.173 vs 0.164 ms), 64-thread CTAs do not.
-    static const int threads = [] { const char* e = getenv("CTVQ_PEER_THREADS"); const int t = e ? atoi(e) : 64; return t >= 32 && t <= 512 ? t : 64; }();
-    size_t blocks = (count + (size_t)threads * 32 - 1) / ((size_t)threads * 32);
-    if (blocks < 1) blocks = 1;
-    if (blocks > 148) blocks = 148;
-    static const int max_blocks = [] { const char* e = getenv("CTVQ_PEER_BLOCKS"); return e ? atoi(e) : 148; }();
-    if (max_blocks >= 1 && blocks > (size_t)max_blocks) blocks = (size_t)max_blocks;
-    peer_allreduce_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    peer_allreduce_kernel<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(t, src);
     const int rc = (int)cudaGetLastError();
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
     return rc;

@@ -332,7 +332,7 @@ int launch_gather(const QuantParams& p, cudaStream_t s) {
     const long long items = p.B * (long long)p.d * (p.HW / (vec ? 4 : 1));
     long long blocks = (items + 256 * 4 - 1) / (256 * 4);
     if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     dim3 grid((unsigned)blocks, (unsigned)p.C);
     if (vec) gather_st_loss_kernel<4><<<grid, 256, 0, s>>>(p);
     else gather_st_loss_kernel<1><<<grid, 256, 0, s>>>(p);
@@ -420,6 +420,7 @@ __global__ void __launch_bounds__(256) backward_kernel(const BwdParams p) {
             if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
         }
     }
+    peer_tail(p.peer, p.gE);  // fused collective (no-op unless ctvq_backward_allreduce armed it)
 }
 
 int launch_backward(const BwdParams& p0, cudaStream_t s) {
@@ -442,7 +443,7 @@ int launch_backward(const BwdParams& p0, cudaStream_t s) {
     p.smem_acc = (acc_bytes <= 64 * 1024 && p.N >= 32768) ? 1 : 0;
     long long blocks = (items + 256 * 4 - 1) / (256 * 4);
     if (blocks < 1) blocks = 1;
-    const long long cap = p.smem_acc ? 148 * 2 : 148 * 16;
+    const long long cap = p.smem_acc ? sm_count() * 2 : sm_count() * 16;
     if (blocks > cap) blocks = cap;
     const size_t sm = p.smem_acc ? acc_bytes : 0;
     if (vec) {
@@ -527,7 +528,7 @@ int launch_reparam_fwd(const float* mu, const float* lv, const float* eps, long 
                                          reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(z)) & 15) == 0);
     long long blocks = ((vec ? n / 4 : n) + 256 * 4 - 1) / (256 * 4);
     if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     reparam_kld_fwd_kernel<<<(unsigned)blocks, 256, 0, s>>>(mu, lv, eps, n, B, z, kld, &ws->kld_acc, &ws->ticket2, vec);
     return (int)cudaGetLastError();
 }
@@ -537,7 +538,7 @@ int launch_reparam_bwd(const float* mu, const float* lv, const float* eps, const
     const long long n = B * (long long)L;
     long long blocks = (n + 256 * 4 - 1) / (256 * 4);
     if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     reparam_kld_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>(mu, lv, eps, g_z, g_kld, n, B, g_mu, g_lv);
     return (int)cudaGetLastError();
 }

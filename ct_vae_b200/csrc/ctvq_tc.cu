@@ -391,6 +391,8 @@ int launch_forward_tc(const QuantParams& p0, cudaStream_t s) {
     if (!g_dbg) {
         int rc = launch_forward_tc_fast(p0, s);
         if (rc != CTVQ_E_UNSUPPORTED) return rc;
+        rc = launch_forward_tc_res(p0, s);  // single codebook resident in shared memory, 16 epilogue warps per tile
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
         rc = launch_forward_tc_c1(p0, s);  // resident-codebook kernels for the configs' own small-K shapes (measured faster there)
         if (rc != CTVQ_E_UNSUPPORTED) return rc;
         rc = launch_forward_tc_stream(p0, s);  // any K: the codebook streams through a TMA ring
@@ -413,7 +415,7 @@ int launch_forward_tc(const QuantParams& p0, cudaStream_t s) {
     if (make_maps(p0, maps, 0) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(vq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return (int)e;
-    int grid = 148 * pl.per_sm;
+    int grid = sm_count() * pl.per_sm;
     if (grid > P.ntiles) grid = P.ntiles;
     vq_fwd_tc_kernel<<<grid, kThreads, pl.smem, s>>>(P, maps);
     return (int)cudaGetLastError();

@@ -353,7 +353,7 @@ int launch_c1(const QuantParams& p0, cudaStream_t s) {
     auto kern = vq_fwd_tc_c1_kernel<D, NK, HWT, NSTAGE, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int grid = 148 * MINB;
+    int grid = sm_count() * MINB;
     if (grid > P.ntiles) grid = P.ntiles;
     kern<<<grid, kCT, smem, s>>>(P, maps);
     return (int)cudaGetLastError();

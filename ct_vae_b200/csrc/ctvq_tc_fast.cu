@@ -447,7 +447,7 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
     auto kern = vq_fwd_tc_fast_kernel<D, NK, HWT, C, CS, NSTAGE, NWG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int grid = 148;
+    int grid = sm_count();
     if (grid > P.ntiles) grid = P.ntiles;
     kern<<<grid, 128 * NWG + 32, smem, s>>>(P, maps);
     return (int)cudaGetLastError();
@@ -455,7 +455,7 @@ int launch_fast(const QuantParams& p0, cudaStream_t s) {
 
 }  // namespace
 
-extern "C" void ctvq_debug_set_fast_trace(unsigned long long* buf) { g_fast_trace = buf; }  // [148*8] device words or null
+extern "C" void ctvq_debug_set_fast_trace(unsigned long long* buf) { g_fast_trace = buf; }  // [SMs*8] device words or null
 
 // Shapes with a specialised kernel; anything else falls through to the generic tcgen05 kernel / SIMT.
 int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {

@@ -499,7 +499,7 @@ int launch_stream(const QuantParams& p0, cudaStream_t s) {
     auto kern = vq_fwd_tc_stream_kernel<D, T, ADB>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int grid = 148;
+    int grid = sm_count();
     if (grid > P.nsuper) grid = P.nsuper;
     kern<<<grid, 128 * T + 96, smem, s>>>(P, maps, bm);
     return (int)cudaGetLastError();

@@ -77,40 +77,32 @@ class CodebookGradComm:
             self._comm = None
 
 
-class _DeviceArray:
-    """Minimal __cuda_array_interface__ carrier so torch can alias memory the C library allocated."""
-
-    def __init__(self, ptr: int, n: int):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3,
-                                         "strides": None}
-
-
 class PeerGradComm:
-    """The same collective WITHOUT NCCL: a one-shot all-reduce over NVLink peer memory (ctvq_peer_* in include/ctvq.h).
+    """The same collective WITHOUT NCCL, fused into the backward kernel: a one-shot all-reduce over NVLink peer memory
+    (ctvq_backward_allreduce / ctvq_peer_allreduce in include/ctvq.h, protocol in csrc/ctvq_peer.cuh).
 
-    The backward kernel writes grad_E straight into this rank's symmetric slot (`grad_buffer`); `allreduce_` launches
-    ONE kernel that handshakes through flag words in the peers' buffers and sums the `world` slots in rank order
-    (bit-identical on every rank), scaled by 1/world.  torch.distributed only carries the 64-byte IPC handles.
-    Single node, world <= 8 (every GPU reaches every peer through NVSwitch)."""
+    The LAST CTA of the backward kernel pushes the finished codebook gradient into every rank's symmetric receive buffer
+    (posted NVLink stores), posts a flag, waits for the peers' flags on local memory and sums the `world` slots in rank
+    order (bit-identical on every rank), scaled by 1/world.  One launch, on the caller's stream: the reduced gradient is
+    ordinary stream-ordered data when backward returns -- no side stream, nothing for the caller to wait on, safe for
+    AccumulateGrad / hooks / clip_grad_norm_ / optimizer.step.  torch.distributed only carries the 64-byte IPC handles.
+    Single node, world <= 8 (every GPU reaches every peer through NVSwitch).
 
-    def __init__(self, count_max: int, device: torch.device, group=None, average: bool = True, overlap: bool = False):
-        """overlap=True launches the all-reduce kernel on a private side stream (ordered after the backward kernel by an
-        event), so it runs underneath whatever the caller enqueues next -- the next forward, the encoder's backward.
-        The caller must then call ``wait()`` before it READS the reduced gradient (optimizer step); the next backward
-        waits by itself before it reuses a slot."""
+    A peer that does not arrive within CTVQ_PEER_TIMEOUT_MS (default 30 s) does not trap the GPU: the kernel finishes and
+    ``check()`` (called by ``close()``, or by the user at any synchronisation point) raises RuntimeError."""
+
+    fuses_backward = True
+
+    def __init__(self, count_max: int, device: torch.device, group=None, average: bool = True):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (it carries the IPC handles)")
         self.group, self.device = group, device
-        self.overlap = bool(overlap)
-        self._side = torch.cuda.Stream(device=device) if overlap else None
-        self._ready = torch.cuda.Event() if overlap else None   # backward kernel finished writing the slot
-        self._done = None                                        # last all-reduce finished (side stream)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         if self.world > 8:
             raise RuntimeError("PeerGradComm covers one NVSwitch box (world <= 8)")
         self.scale = 1.0 / self.world if average else 1.0
-        self.count_max = int(count_max)
+        self.count_max = (int(count_max) + 3) // 4 * 4
         self.epoch = 0
         self.launches = 0
         L = _lib.lib()
@@ -133,54 +125,48 @@ class PeerGradComm:
         self._table = (ctypes.c_void_p * self.world)(*[p.value for p in self._peers])
         dist.barrier(group=group)  # every rank has mapped every buffer before anyone signals
 
-    def grad_buffer(self, shape) -> torch.Tensor:
-        """Tensor aliasing the slot the NEXT all-reduce will read (the backward kernel's gE_out)."""
-        n = 1
-        for s in shape:
-            n *= int(s)
-        if n > self.count_max:
-            raise RuntimeError(f"codebook gradient ({n} floats) exceeds the symmetric buffer ({self.count_max})")
-        if self._done is not None:
-            # the slot about to be rewritten was last read by the peers during all-reduce (epoch - 1); our all-reduce of
-            # `epoch` completing proves every peer has finished that one
-            torch.cuda.current_stream(self.device).wait_event(self._done)
-        slot = _lib.lib().ctvq_peer_slot(self._own, self.count_max, self.epoch + 1)
-        return torch.as_tensor(_DeviceArray(slot, n), device=self.device).view(*shape)
+    def peer_args(self, count: int):
+        """-> (table, world, rank, count_max, epoch, scale) for the next collective (advances the epoch)."""
+        if count > self.count_max:
+            raise RuntimeError(f"codebook gradient ({count} floats) exceeds the symmetric buffer ({self.count_max})")
+        self.epoch += 1
+        self.launches += 1
+        return self._table, self.world, self.rank, self.count_max, self.epoch, self.scale
 
     def allreduce_(self, grad: torch.Tensor) -> torch.Tensor:
-        self.epoch += 1
-        out = torch.empty(grad.shape, dtype=torch.float32, device=self.device)
-        if self.overlap:
-            main = torch.cuda.current_stream(self.device)
-            self._ready.record(main)
-            self._side.wait_event(self._ready)
-            sp = self._side.cuda_stream
-            out.record_stream(self._side)
-        else:
-            sp = _lib.stream_ptr(self.device)
-        rc = _lib.lib().ctvq_peer_allreduce(self._table, self.world, self.rank, self.count_max, grad.numel(),
-                                            self.epoch, self.scale, out.data_ptr(), self.device.index, sp)
+        """Stand-alone form (the local gradient already exists): one small kernel on the current stream."""
+        g = grad.detach().contiguous()
+        out = torch.empty_like(g, dtype=torch.float32)
+        table, world, rank, cmax, epoch, scale = self.peer_args(g.numel())
+        sp = _lib.stream_ptr(self.device)
+        ws = _lib.workspace(self.device, sp)
+        rc = _lib.lib().ctvq_peer_allreduce(table, world, rank, cmax, g.data_ptr(), g.numel(), epoch, scale,
+                                            out.data_ptr(), ws.data_ptr(), ws.numel(), self.device.index, sp)
         _lib.check(rc, "ctvq_peer_allreduce")
-        if self.overlap:
-            self._done = torch.cuda.Event()
-            self._done.record(self._side)
-        self.launches += 1
         return out
 
     def wait(self) -> None:
-        """Make the current stream wait for the last all-reduce (no-op without overlap)."""
-        if self._done is not None:
-            torch.cuda.current_stream(self.device).wait_event(self._done)
+        """Kept for callers written against the round-1 interface: the collective is stream-ordered now, nothing to wait for."""
+
+    def check(self) -> None:
+        """Synchronises; raises when a peer timed out in any collective since the last check."""
+        for (idx, sp), ws in list(_lib._workspaces.items()):
+            if idx == self.device.index and _lib.read_and_clear_err(ws, self.device, sp) & 2:
+                raise RuntimeError("ct_vae_b200: a peer rank did not reach the codebook-gradient all-reduce within "
+                                   "CTVQ_PEER_TIMEOUT_MS; the reduced gradient of that step is incomplete")
 
     def close(self):
         L = _lib.lib()
         torch.cuda.synchronize(self.device)
-        for r, p in enumerate(self._peers):
-            if r != self.rank and p is not None:
-                L.ctvq_peer_close(p, self.device.index)
-        if self._own is not None:
-            L.ctvq_peer_free(self._own, self.device.index)
-        self._peers, self._own = [], None
+        try:
+            self.check()
+        finally:
+            for r, p in enumerate(self._peers):
+                if r != self.rank and p is not None:
+                    L.ctvq_peer_close(p, self.device.index)
+            if self._own is not None:
+                L.ctvq_peer_free(self._own, self.device.index)
+            self._peers, self._own = [], None
 
 
 def shard_batch(global_batch: int, world: int, rank: int):

@@ -145,10 +145,7 @@ class _Quantize(torch.autograd.Function):
         if ctx.empty:
             beta, cs, b, dtot, h, w, c, d, k, comm = ctx.meta
             dev = ctx.dev
-            if comm is not None and hasattr(comm, "grad_buffer"):
-                ge = comm.grad_buffer((c, k, d)).zero_()
-            else:
-                ge = torch.zeros((c, k, d), dtype=torch.float32, device=dev)
+            ge = torch.zeros((c, k, d), dtype=torch.float32, device=dev)
             if comm is not None:
                 ge = comm.allreduce_(ge)
             gz = torch.zeros((b, dtot, h, w), dtype=ctx.io_dtype, device=dev)
@@ -164,19 +161,28 @@ class _Quantize(torch.autograd.Function):
             g_out = g_out.contiguous().float()
             go_ptr = g_out.data_ptr()
         gz = torch.empty_like(z)
-        if comm is not None and hasattr(comm, "grad_buffer"):
-            ge = comm.grad_buffer((c, k, d))  # symmetric NVLink-mapped slot: the kernel writes where peers read
-        else:
-            ge = torch.empty((c, k, d), dtype=torch.float32, device=dev)
+        ge = torch.empty((c, k, d), dtype=torch.float32, device=dev)
         sp = _lib.stream_ptr(dev)
         ws = _lib.workspace(dev, sp, c, k, d)
-        rc = _lib.lib().ctvq_backward(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), go_ptr, g_loss.data_ptr(), b,
-                                      dtot, h * w, c, d, k, cs, _lib.F32, beta, gz.data_ptr(), ge.data_ptr(),
-                                      ws.data_ptr(), ws.numel(), dev.index, sp)
-        _lib.check(rc, "ctvq_backward")
+        if comm is not None and getattr(comm, "fuses_backward", False):
+            # backward + the path's one collective in ONE launch: the kernel's last CTA all-reduces grad_E over NVLink
+            table, world, rank, cmax, epoch, scale = comm.peer_args(c * k * d)
+            red = torch.empty((c, k, d), dtype=torch.float32, device=dev)
+            rc = _lib.lib().ctvq_backward_allreduce(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), go_ptr,
+                                                    g_loss.data_ptr(), b, dtot, h * w, c, d, k, cs, _lib.F32, beta,
+                                                    gz.data_ptr(), ge.data_ptr(), table, world, rank, cmax, epoch, scale,
+                                                    red.data_ptr(), ws.data_ptr(), ws.numel(), dev.index, sp)
+            _lib.check(rc, "ctvq_backward_allreduce")
+            ge = red
+            comm = None
+        else:
+            rc = _lib.lib().ctvq_backward(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), go_ptr, g_loss.data_ptr(),
+                                          b, dtot, h * w, c, d, k, cs, _lib.F32, beta, gz.data_ptr(), ge.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), dev.index, sp)
+            _lib.check(rc, "ctvq_backward")
         _lib.maybe_validate(ws, dev, sp, "quantiser backward")
         if comm is not None:
-            ge = comm.allreduce_(ge)  # the one collective of the path, on the backward kernel's stream
+            ge = comm.allreduce_(ge)  # the one collective of the path (NCCL), on the backward kernel's stream
         if ctx.io_dtype == torch.bfloat16:
             gz = gz.to(torch.bfloat16)
         return (gz, None, None, None, None, None, *ge.unbind(0))

@@ -160,12 +160,16 @@ int ctvq_nccl_comm_destroy(void* comm);
 /* sum over ranks then multiply by `scale` (1/world = DDP's gradient averaging), in place, on `stream`. */
 int ctvq_allreduce_codebook_grad(void* comm, float* gE, size_t count, float scale, int device, void* stream);
 
-/* One-shot all-reduce of the codebook gradient over NVLink peer memory (no NCCL on the path): every rank owns a
- * "symmetric" buffer (two gradient slots of `count_max` floats + `world` flag words) that its peers map through CUDA
- * IPC.  ctvq_backward writes grad_E straight into the current slot; ctvq_peer_allreduce then (1) posts this rank's
- * epoch into every peer's flag row, (2) waits until all peers' epochs arrived, (3) sums the `world` slots in rank
- * order (bit-identical on every rank) scaled by `scale` into `out`.  Slots alternate by epoch parity, which makes a
- * second barrier unnecessary.  The handle exchange is the caller's job (64-byte cudaIpcMemHandle_t per rank). */
+/* One-shot all-reduce of the codebook gradient over NVLink peer memory (no NCCL on the path), normally FUSED into the
+ * backward kernel: every rank owns a "symmetric" buffer (2 parities x `world` receive slots of `count_max` floats +
+ * `world` flag words) that its peers map through CUDA IPC.  Push protocol (csrc/ctvq_peer.cuh): once the local partial
+ * gradient is complete, ONE CTA (1) stores it into slot [epoch parity][rank] of every rank's buffer (posted NVLink
+ * writes), (2) fences and posts `epoch` into every rank's flag row, (3) waits until its own flag row shows `epoch` for
+ * every rank (local polling), (4) sums the `world` local slots in rank order, times `scale`, into `out` -- bit-identical
+ * on every rank.  Slots alternate by epoch parity, which makes a second barrier unnecessary; epochs must increase by one
+ * per collective on every rank, starting at 1.  A peer that does not arrive within CTVQ_PEER_TIMEOUT_MS (env, default
+ * 30000) does not trap: bit 1 of the workspace error word is set (ctvq_read_and_clear_err) and the kernel finishes.
+ * The handle exchange is the caller's job (64-byte cudaIpcMemHandle_t per rank); count_max must be a multiple of 4. */
 #define CTVQ_MAX_PEERS 8
 #define CTVQ_IPC_HANDLE_BYTES 64
 size_t ctvq_peer_buffer_bytes(size_t count_max, int world);
@@ -174,11 +178,19 @@ int ctvq_peer_free(void* dev_ptr, int device);
 int ctvq_peer_export(void* dev_ptr, void* handle64_out, int device);
 int ctvq_peer_import(const void* handle64, void** dev_ptr_out, int device);
 int ctvq_peer_close(void* dev_ptr, int device);
-/* peer_bufs: host array of `world` device pointers (entry `rank` = this rank's own buffer).  Returns the slot of
- * epoch `epoch` through ctvq_peer_slot(). */
-float* ctvq_peer_slot(void* own_buf, size_t count_max, unsigned epoch);
-int ctvq_peer_allreduce(void* const* peer_bufs, int world, int rank, size_t count_max, size_t count, unsigned epoch,
-                        float scale, float* out, int device, void* stream);
+/* Stand-alone collective on an already complete local gradient `src` [count] (one 512-thread CTA).
+ * peer_bufs: host array of `world` device pointers (entry `rank` = this rank's own buffer). */
+int ctvq_peer_allreduce(void* const* peer_bufs, int world, int rank, size_t count_max, const float* src, size_t count,
+                        unsigned epoch, float scale, float* out, void* workspace, size_t ws_bytes, int device,
+                        void* stream);
+/* backward + all-reduce in ONE launch: ctvq_backward (above) whose last CTA runs the collective on the finished
+ * gE_local [C,K,d] and leaves sum_over_ranks(gE) * scale in gE_reduced_out [C,K,d] (scale = 1/world reproduces DDP's
+ * gradient averaging, run.py:99).  Works with whichever backward kernel the shape dispatches to. */
+int ctvq_backward_allreduce(const void* z, const void* const* codebooks, const int64_t* idx, const void* g_out,
+                            const float* g_loss, int64_t B, int Dtot, int HW, int C, int d, int K, int chan_stride,
+                            int dtype, float beta, void* gz_out, float* gE_local, void* const* peer_bufs, int world,
+                            int rank, size_t count_max, unsigned epoch, float scale, float* gE_reduced_out,
+                            void* workspace, size_t ws_bytes, int device, void* stream);
 
 #ifdef __cplusplus
 }
