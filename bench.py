@@ -7,16 +7,27 @@
 A *step* is one pass of the hot path over one batch of synthetic latents: the multi-codebook quantiser of
 configs/mcq_vae.yaml (C=4 codebooks, d=32, K=64 codes, encoder latents [B,128,8,8]) run forward (argmin +
 gather + losses + straight-through) and backward (straight-through/commitment gradient + codebook-gradient
-scatter-add), plus — for N>1 — the NCCL all-reduce of the stacked codebook gradient (the path's only
-collective).  ``value`` = latent vectors (rows of the [B*H*W, 128] latent matrix, each quantised by C
-codebooks) processed per second by the whole job with inputs resident in HBM; ``e2e`` = the same metric
-through the public nn.Module API with the step's latents arriving from pinned HOST memory and the loss read
-back to the host inside the timed region.  The same JSON line also carries the MCQ-VAE training-step
-throughput (``train``: images/s, the second half of BASELINE.json's metric), the roofline of the dominant
-kernel and the CPU baseline.
+scatter-add), plus -- for N>1 -- the all-reduce of the stacked codebook gradient (the path's only collective),
+fused into the backward kernel's last CTA.  ``value`` = latent vectors (rows of the [B*H*W, 128] latent matrix,
+each quantised by C codebooks) processed per second by the whole job with inputs resident in HBM; ``e2e`` = the
+same metric through the public nn.Module API with the step's latents arriving from pinned HOST memory and the
+quantised output, the indices and the loss copied back to the host inside the timed region.
+
+The same JSON line also carries (all measured in this run, nothing quoted):
+  roofline / kernels   per-kernel CUDA-event times of forward and backward, algorithmic bytes / time / measured peak
+  sub_records          configs 1, 3, 5 of BASELINE.json and two sweep points (a low-K HBM-bound one, the K=16384
+                       tensor-bound one), each with its own roofline fraction, plus CUDA-graph latencies at the
+                       configs' own batch sizes
+  parity               near-tie rows counted by the kernel and index mismatches against the reference arithmetic on the
+                       CPU sample (north_star: "counted and reported, not hidden")
+  collective_check     N>1: the reduced codebook gradient against the rank-ordered sum / world
+  train                MCQ-VAE training images/s (second half of BASELINE.json's metric) and, at N=1, the same shell with
+                       the reference's stock-torch quantiser on the same GPU
+  cpu_baseline / gpu_eager_baseline   the reference's op sequence on host cores / in stock torch eager on this GPU
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -58,14 +69,15 @@ def emit(line: dict):
 
 
 def peaks():
+    """-> (HBM GB/s, tf32 TFLOP/s, source).  tf32 is taken as half the measured dense bf16 burst figure."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(d["hbm_gbs"]), float(d["bf16_tflops"]) / 2.0, "measured (MEASURED_PEAKS.json; tf32 = bf16 burst / 2)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1590.0 / 2.0, "fallback (B200_PROFILING.md; tf32 = bf16 / 2)"
 
 
 def algorithmic_bytes_per_row(C, d, Dtot, cs=1):
@@ -79,7 +91,8 @@ def algorithmic_bytes_per_row(C, d, Dtot, cs=1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks/throttle reasons sampled DURING the GPU measurements (B200_PROFILING.md): started before the
+    warm-up, stopped after the last measured quantity, so the K timed steps lie inside the sampled window."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -95,10 +108,10 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "samples_under_load": 0}
         if self.p is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(5)
@@ -107,21 +120,77 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.strip().lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 continue
         if sm:
-            hi = [s for s in sm if s >= 0.5 * max(sm)]  # samples under load
-            out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            load = [s for s, w in zip(sm, pw) if w >= 0.5 * max(pw)] or sm  # samples taken while the GPU was drawing power
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       samples_under_load=len(load), power_w_max=max(pw))
         return out
+
+
+def timed_ms(fn, dev, min_ms=100.0, warmup=3, flush=None, max_iters=100000):
+    """Mean CUDA-event time of fn() over as many back-to-back calls as it takes to fill ``min_ms`` of device time (so the
+    clock sampler sees the load); with ``flush`` the L2 is overwritten before every call and each call is timed alone."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    if flush is not None:
+        ts = []
+        total = 0.0
+        while total < min_ms and len(ts) < 400:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+            total += ts[-1] + 0.1
+        return statistics.mean(ts)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    one = max(a.elapsed_time(b), 1e-3)
+    iters = int(min(max_iters, max(5, math.ceil(min_ms / one))))
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b) / iters
+
+
+def numa_local(dev_index):
+    """Best effort: pin this process to the CPUs local to the GPU before pinned host buffers are allocated (first-touch
+    places them on that node; all ranks allocating on node 0 halves the per-GPU H2D rate at N=8)."""
+    try:
+        prop = torch.cuda.get_device_properties(dev_index)
+        bus = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        path = f"/sys/bus/pci/devices/{bus}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"bus": bus, "cpus": len(cpus)}
+    except Exception as e:
+        return {"error": repr(e)[:80]}
+    return None
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -134,92 +203,121 @@ def cpu_quantiser_step(O, z, books, g_out, beta):
     return loss
 
 
-def cpu_baseline(budget_s=12.0, batch=1024, max_reps=20):
-    """Oracle port (same ATen CPU operators as the reference's modules) on a bounded sample of the workload."""
+def cpu_baseline(budget_s=15.0, batches=(1024, 4096), max_reps=20):
+    """Oracle port (same ATen CPU operators as the reference's modules) on bounded samples of the workload; two sample
+    sizes show that CPU throughput does not depend on the batch (the GPU arm runs 16 384 images per step)."""
     from oracle import ctvq_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     C, K, D, H, W = (CFG[k] for k in "CKDHW")
-    torch.manual_seed(1320)
-    z = torch.randn(batch, D, H, W)
-    books = [torch.randn(K, D // C) * 0.5 for _ in range(C)]
-    g_out = torch.randn(batch, D, H, W)
-    cpu_quantiser_step(O, z, books, g_out, CFG["beta"])  # warm-up
-    times, t_all = [], time.perf_counter()
-    while len(times) < max_reps and (time.perf_counter() - t_all) < budget_s:
-        t0 = time.perf_counter()
-        cpu_quantiser_step(O, z, books, g_out, CFG["beta"])
-        times.append(time.perf_counter() - t0)
-    best = min(times)
-    return {"value": batch * H * W / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle/ctvq_oracle.py (reference ATen CPU ops) fwd+bwd on {batch} images = {batch * H * W} "
-                      f"latents, best of {len(times)} reps", "ms_per_sample": best * 1e3}
+    out = {}
+    for batch in batches:
+        torch.manual_seed(1320)
+        z = torch.randn(batch, D, H, W)
+        books = [torch.randn(K, D // C) * 0.5 for _ in range(C)]
+        g_out = torch.randn(batch, D, H, W)
+        cpu_quantiser_step(O, z, books, g_out, CFG["beta"])  # warm-up
+        times, t_all = [], time.perf_counter()
+        while len(times) < max_reps and (time.perf_counter() - t_all) < budget_s / len(batches):
+            t0 = time.perf_counter()
+            cpu_quantiser_step(O, z, books, g_out, CFG["beta"])
+            times.append(time.perf_counter() - t0)
+        out[batch] = (batch * H * W / min(times), len(times), min(times))
+    b0 = batches[0]
+    return {"value": out[b0][0], "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle/ctvq_oracle.py (reference ATen CPU ops) fwd+bwd on {b0} images = {b0 * H * W} "
+                      f"latents, best of {out[b0][1]} reps", "ms_per_sample": out[b0][2] * 1e3,
+            "by_batch": {str(b): {"latents_per_s": v[0], "reps": v[1]} for b, v in out.items()}}
 
 
-def torch_eager_gpu_baseline(dev, batch=4096, reps=5):
-    """The reference's op sequence (models/mcq_vae.py:26-64,100-127: permute, matmul distances, argmin, one-hot scatter,
-    one-hot matmul, two mse_loss, straight-through, permute back; autograd backward) as STOCK torch eager on the same
-    B200 — the honest GPU baseline the fused kernels replace.  Plain library calls, none of our kernels."""
-    import torch.nn.functional as F
+def parity_report(m, dev, images=512):
+    """north_star: near-ties are counted and reported.  On a CPU-sized sample of the benchmark's own input
+    distribution: the kernel's near-tie counter, and how many indices differ from the reference arithmetic (oracle port:
+    ATen sgemm order) -- every such row must be a counted near-tie."""
+    from oracle import ctvq_oracle as O
     C, K, D, H, W = (CFG[k] for k in "CKDHW")
-    d = D // C
-    torch.manual_seed(1320)
-    books = [(torch.randn(K, d, device=dev) * 0.5).requires_grad_(True) for _ in range(C)]
-    z = torch.randn(batch, D, H, W, device=dev, requires_grad=True)
-    g_out = torch.randn(batch, D, H, W, device=dev)
+    torch.manual_seed(4242)
+    z = torch.randn(images, D, H, W)
+    books = [q.embedding.weight.detach().cpu() for q in m.quantizers]
+    m.near_tie_rows(reset=True)
+    with torch.no_grad():
+        inds = m.compute_inds(z.to(dev)).cpu()
+    near = m.near_tie_rows(reset=True)
+    ref = O.mcq_compute_inds(z, books)
+    mism = int((inds != ref).sum())
+    return {"rows": images * H * W * C, "near_tie_rows": int(near), "index_mismatch_vs_reference": mism,
+            "definition": "near-tie: relative top-2 distance gap <= 1e-6 (include/ctvq.h); reference = oracle port "
+                          "(ATen CPU arithmetic of models/mcq_vae.py:26-39)"}
 
-    def step():
+
+class EagerMCQ(torch.nn.Module):
+    """The reference's multi-codebook quantiser as STOCK torch ops (models/mcq_vae.py:26-64,100-137 restated: permute,
+    matmul distances, argmin, one-hot scatter, one-hot matmul, two mse_loss, straight-through, permute back) -- the GPU
+    baseline the fused kernels replace.  Plain library calls, none of our kernels."""
+
+    def __init__(self, K, D, C, beta):
+        super().__init__()
+        self.K, self.d, self.C, self.beta = K, D // C, C, beta
+        self.books = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(K, D // C) * 0.5) for _ in range(C)])
+
+    def forward(self, z):
+        import torch.nn.functional as F
         outs, total = [], 0
-        for i, e in enumerate(books):
-            lat = z[:, i:i + d].permute(0, 2, 3, 1).contiguous()
-            flat = lat.view(-1, d)
+        for i, e in enumerate(self.books):
+            lat = z[:, i:i + self.d].permute(0, 2, 3, 1).contiguous()
+            flat = lat.view(-1, self.d)
             dist = torch.sum(flat ** 2, dim=1, keepdim=True) + torch.sum(e ** 2, dim=1) - 2 * torch.matmul(flat, e.t())
             inds = torch.argmin(dist, dim=1).unsqueeze(1)
-            one_hot = torch.zeros(inds.size(0), K, device=dev)
+            one_hot = torch.zeros(inds.size(0), self.K, device=z.device)
             one_hot.scatter_(1, inds, 1)
             q = torch.matmul(one_hot, e).view(lat.shape)
-            total = total + F.mse_loss(q.detach(), lat) * CFG["beta"] + F.mse_loss(q, lat.detach())
+            total = total + F.mse_loss(q.detach(), lat) * self.beta + F.mse_loss(q, lat.detach())
             outs.append((lat + (q - lat).detach()).permute(0, 3, 1, 2).contiguous())
-        out = torch.cat(outs, 1)
-        torch.autograd.backward([out, total], [g_out, torch.ones((), device=dev)])
+        return torch.cat(outs, 1), total
+
+
+def torch_eager_gpu_baseline(dev, batch):
+    """EagerMCQ forward + autograd backward at the benchmark's own batch on the same B200."""
+    C, K, D, H, W = (CFG[k] for k in "CKDHW")
+    torch.manual_seed(1320)
+    m = EagerMCQ(K, D, C, CFG["beta"]).to(dev)
+    z = torch.randn(batch, D, H, W, device=dev, requires_grad=True)
+    g_out = torch.randn(batch, D, H, W, device=dev)
+    one = torch.ones((), device=dev)
+
+    def step():
+        out, total = m(z)
+        torch.autograd.backward([out, total], [g_out, one])
         z.grad = None
-        for e in books:
+        for e in m.books:
             e.grad = None
 
-    for _ in range(2):
-        step()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / reps
+    ms = timed_ms(step, dev, min_ms=100.0, warmup=2)
     return {"value": batch * H * W / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": batch,
-            "what": "reference op sequence in stock torch eager (fp32, TF32 off) on this GPU"}
+            "what": "reference op sequence in stock torch eager (fp32, TF32 off) on this GPU, same batch as the GPU arm"}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path, all host threads, same metric/unit."""
+    """--impl reference: the reference's CPU implementation of the path, all host threads, same metric / unit / batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import ctvq_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     C, K, D, H, W = (CFG[k] for k in "CKDHW")
-    batch = args.ref_batch
+    batch = args.ref_batch or args.batch
     torch.manual_seed(1320)
     z = torch.randn(batch, D, H, W)
     books = [torch.randn(K, D // C) * 0.5 for _ in range(C)]
     g_out = torch.randn(batch, D, H, W)
-    for _ in range(max(1, args.warmup)):
+    for _ in range(max(1, min(args.warmup, 2))):
         cpu_quantiser_step(O, z, books, g_out, CFG["beta"])
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_quantiser_step(O, z, books, g_out, CFG["beta"])
     dt = time.perf_counter() - t0
     val = batch * H * W * args.steps / dt
-    sample = f"{batch} images ({batch * H * W} latents) per step: bounded sample of the workload"
+    sample = f"{batch} images ({batch * H * W} latents) per step: the GPU arm's own batch" if batch == args.batch else \
+             f"{batch} images ({batch * H * W} latents) per step: bounded sample of the workload"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -235,11 +333,148 @@ def workload_config(batch_per_gpu, n_gpus):
     C, K, D, H, W = (CFG[k] for k in "CKDHW")
     return {"workload": "configs[1] MCQ-VAE quantiser (configs/mcq_vae.yaml): C=4 codebooks x K=64 codes x d=32, "
                         "latents [B,128,8,8] fp32, forward (argmin+gather+loss+straight-through) + backward "
-                        "(grad_z + codebook-grad scatter-add)" + (" + NCCL all-reduce of grad_E" if n_gpus > 1 else ""),
+                        "(grad_z + codebook-grad scatter-add)" + (" + all-reduce of grad_E" if n_gpus > 1 else ""),
             "batch_per_gpu": batch_per_gpu, "latents_per_gpu": batch_per_gpu * H * W, "codebooks": C,
             "num_embeddings": K, "embedding_dim": D, "chan_stride": 1,
             "parallelism": f"batch-sharded x{n_gpus}, codebooks replicated",
             "l2": "inputs larger than L2 (no flush needed)" if batch_per_gpu * D * H * W * 4 > 200e6 else "L2 flushed between steps"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# sub-records: the other configs of BASELINE.json, each with its own roofline fraction
+# ------------------------------------------------------------------------------------------------------
+def quantiser_record(pkg, _lib, dev, name, what, N, D, HW, C, K, kind, hbm_peak, tc_peak, flush):
+    d = D // C
+    side = int(round(HW ** 0.5))
+    B = N // HW
+    torch.manual_seed(0)
+    m = (pkg.MultipleCodebookVectorQuantizer(K, D, C) if C > 1 else pkg.VectorQuantizerMS(K, D)).to(dev)
+    books = [q.embedding.weight for q in m.quantizers] if C > 1 else [m.embedding.weight]
+    if kind == "trained":
+        for e in books:
+            e.data = torch.randn(K, d, device=dev) * 0.5
+    z = torch.randn(B, D, side, side, device=dev).requires_grad_(True)
+    g_out = torch.randn(B, C * d, side, side, device=dev)
+    g_loss = torch.ones((), device=dev)
+    fb, bb = algorithmic_bytes_per_row(C, d, D)
+    fl = flush if N * D * 4 < 200e6 else None
+
+    def fwd():
+        with torch.no_grad():
+            return m(z, inds=True)
+
+    def fwdbwd():
+        out, loss = m(z)
+        torch.autograd.backward([out, loss], [g_out, g_loss])
+        z.grad = None
+        for e in books:
+            e.grad = None
+
+    t_f = timed_ms(fwd, dev, flush=fl)
+    path = {1: "simt", 2: "tcgen05"}.get(_lib.last_path(), "?")
+    t_fb = timed_ms(fwdbwd, dev, flush=fl)
+    flops = 2.0 * N * K * d * C
+    out = {"name": name, "what": what, "rows": N, "D": D, "HW": HW, "C": C, "K": K, "codebook": kind, "path": path,
+           "l2": "flushed between calls" if fl is not None else "inputs larger than L2"}
+    for tag, t, byts in (("fwd", t_f, fb * N), ("fwd_bwd", t_fb, (fb + bb) * N)):
+        t_hbm, t_tc = byts / (hbm_peak * 1e9) * 1e3, flops / (tc_peak * 1e12) * 1e3
+        out[tag] = {"ms": t, "latents_per_s": N / (t * 1e-3), "alg_bytes": byts, "gbs": byts / (t * 1e-3) / 1e9,
+                    "hbm_frac": t_hbm / t, "tflops": flops / (t * 1e-3) / 1e12, "tensor_frac": t_tc / t,
+                    "bound": "hbm" if t_hbm >= t_tc else "tensor", "frac": max(t_hbm, t_tc) / t}
+    m.near_tie_rows(reset=True)
+    fwd()
+    out["near_tie_rows"] = m.near_tie_rows()  # of ONE forward over these rows (kernel counter, include/ctvq.h)
+    return out
+
+
+def gaussian_record(dev, B, L, hbm_peak, flush):
+    from ct_vae_b200 import gaussian
+    mu = torch.randn(B, L, device=dev, requires_grad=True)
+    lv = (torch.randn(B, L, device=dev) * 0.5).requires_grad_(True)
+    eps = torch.randn(B, L, device=dev)
+    gz = torch.randn(B, L, device=dev)
+    gk = torch.ones((), device=dev)
+    fl = flush if B * L * 16 < 200e6 else None
+
+    def f():
+        with torch.no_grad():
+            return gaussian.reparam_kld(mu, lv, eps)
+
+    def fb():
+        zz, kk = gaussian.reparam_kld(mu, lv, eps)
+        torch.autograd.backward([zz, kk], [gz, gk])
+        mu.grad = None
+        lv.grad = None
+
+    tf_, tfb = timed_ms(f, dev, flush=fl), timed_ms(fb, dev, flush=fl)
+    return {"name": f"cfg5_gaussian_B{B}", "what": "configs[4]: fused reparameterise + KL (models/vanilla_vae.py:107-117,143), "
+            f"mu/logvar/eps [{B},{L}] fp32; 16 B/element forward, +24 B backward", "elements": B * L,
+            "fwd": {"ms": tf_, "gbs": 16 * B * L / tf_ / 1e6, "frac": 16 * B * L / tf_ / 1e6 / hbm_peak, "bound": "hbm"},
+            "fwd_bwd": {"ms": tfb, "gbs": 40 * B * L / tfb / 1e6, "frac": 40 * B * L / tfb / 1e6 / hbm_peak, "bound": "hbm"}}
+
+
+def graph_latency(pkg, dev, name, B, D, H, W, C, K, pair=False):
+    """The configs' OWN batch sizes are launch-bound: forward + backward replayed from a CUDA graph, microseconds."""
+    d = D // C
+    m = (pkg.MultipleCodebookVectorQuantizer(K, D, C) if C > 1 or pair else pkg.VectorQuantizerMS(K, D)).to(dev)
+    z = torch.randn(B, D, H, W, device=dev, requires_grad=True)
+    y = torch.randn(B, D, H, W, device=dev)
+    g = torch.randn(B, C * d, H, W, device=dev)
+    gl = torch.ones((), device=dev)
+
+    def fb():
+        if pair:  # CT 'action' mode: both members of the pair in one argmin launch, then the gather by indices
+            ix, iy = m.compute_inds_pair(z.detach(), y)
+            o, l = m.compute_latents(z, ix)
+        else:
+            o, l = m(z)
+        torch.autograd.backward([o, l], [g, gl])
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fb()
+            z.grad = None
+            m.zero_grad(set_to_none=True)
+    torch.cuda.current_stream().wait_stream(s)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        fb()
+    us = timed_ms(gr.replay, dev, min_ms=50.0) * 1e3
+    return {"name": name, "rows": B * H * W * (2 if pair else 1), "fwd_bwd_graph_us": us}
+
+
+def sub_records(pkg, _lib, dev, hbm_peak, tc_peak):
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    recs = []
+    for args in (
+        ("cfg1_vqvae", "configs[0] shape at a bandwidth-meaningful batch: VectorQuantizer K=512, D=64 (configs/vq_vae.yaml), "
+         "latents [4096,64,16,16], reference init codebook", 1 << 20, 64, 256, 1, 512, "init"),
+        ("cfg3_ct_mcq", "configs[2] quantiser: C=1, d=128, K=64 (configs/ct_mcq_vae.yaml), latents [16384,128,8,8]",
+         1 << 20, 128, 64, 1, 64, "trained"),
+        ("sweep_lowK_d32_k256", "configs[3] sweep point, HBM-bound: N=1M, D=32, K=256", 1 << 20, 32, 256, 1, 256, "trained"),
+        ("sweep_highK_d256_k16384", "configs[3] sweep point, tensor-bound: N=64k, D=256, K=16384", 1 << 16, 256, 256, 1, 16384,
+         "trained"),
+    ):
+        try:
+            recs.append(quantiser_record(pkg, _lib, dev, *args, hbm_peak, tc_peak, flush))
+        except Exception as e:  # a failing sub-record must not take the headline down; it is visible in the line
+            recs.append({"name": args[0], "error": repr(e)[:200]})
+    for B in (4096, 1 << 17):
+        try:
+            recs.append(gaussian_record(dev, B, 128, hbm_peak, flush))
+        except Exception as e:
+            recs.append({"name": f"cfg5_gaussian_B{B}", "error": repr(e)[:200]})
+    lat = []
+    for a in (("cfg1_B64", 64, 64, 16, 16, 1, 512, False), ("cfg2_B64", 64, 128, 8, 8, 4, 64, False),
+              ("cfg3_pair_B16", 16, 128, 8, 8, 1, 64, True)):
+        try:
+            lat.append(graph_latency(pkg, dev, *a))
+        except Exception as e:
+            lat.append({"name": a[0], "error": repr(e)[:200]})
+    del flush
+    return recs, lat
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -252,12 +487,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="images per GPU per step (x64 latents each)")
-    ap.add_argument("--ref-batch", type=int, default=1024)
+    ap.add_argument("--ref-batch", type=int, default=0, help="reference arm: images per step (0 = the GPU arm's batch)")
     ap.add_argument("--train-batch", type=int, default=64, help="MCQ-VAE train-step images per GPU (configs/mcq_vae.yaml:15)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
-                    help="N>1: one-shot NVLink peer-memory all-reduce of grad_E (default) or NCCL")
+                    help="N>1: one-shot NVLink peer-memory all-reduce of grad_E fused into the backward (default) or NCCL")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sub-records (other configs, latencies)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -277,6 +513,7 @@ def main():
         raise RuntimeError("bench.py (our arm) needs a CUDA device: there is no CPU fallback")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = numa_local(local)
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -317,20 +554,16 @@ def main():
             p.grad = None
         return loss
 
-    def comm_wait():  # the overlapped all-reduce of the last step belongs to the timed region
-        if comm is not None and hasattr(comm, "wait"):
-            comm.wait()
-
     def sync_all():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step(z)
     sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
     small = B * D * H * W * 4 <= 200e6  # inputs do not exceed L2 (126 MB) comfortably: flush it between steps
     if small:
         flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -339,7 +572,6 @@ def main():
             flush.zero_()
             a.record()
             step(z)
-            comm_wait()
             b.record()
         sync_all()
         ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -349,14 +581,15 @@ def main():
         e0.record()
         for _ in range(args.steps):
             step(z)
-        comm_wait()
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
-    # per-kernel durations over the same steps (events on the launching stream = torch's current stream)
-    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for i in range(args.steps):
+    # per-kernel durations (events on the launching stream = torch's current stream), >= 100 ms of load per quantity
+    reps = max(args.steps, int(math.ceil(100.0 / max(ms / args.steps, 1e-3))))
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    m.near_tie_rows(reset=True)
+    for i in range(reps):
         fwd_ev[i][0].record()
         out, loss = m(z)
         fwd_ev[i][1].record()
@@ -367,7 +600,7 @@ def main():
         for p in params:
             p.grad = None
     sync_all()
-    clocks = sampler.stop() if sampler else None
+    near_per_step = m.near_tie_rows(reset=True) / reps
     fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
     bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in bwd_ev)
     fwd_path = _lib.last_path()
@@ -413,18 +646,25 @@ def main():
         if rel > 1e-5 or (isinstance(comm, PeerGradComm) and not identical):
             raise RuntimeError(f"collective check failed: {collective_check}")
 
-    # ---- e2e: public API, latents from pinned host memory each step, loss read back --------------------
+    # ---- e2e: public API; latents from pinned host memory each step; output, indices and loss copied back -------------
     e2e_steps = max(3, min(args.steps, 10))
     host_z = torch.randn(B, D, H, W).pin_memory()
+    host_q = torch.empty(B, D, H, W).pin_memory()
+    host_i = torch.empty(B, C, H, W, dtype=torch.int64).pin_memory()
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
     dz = torch.empty(B, D, H, W, device=dev, requires_grad=True)
 
     def e2e_step():
         with torch.no_grad():
             dz.copy_(host_z, non_blocking=True)
-        loss = step(dz)
-        comm_wait()
+        out, loss, inds = m(dz, inds=True)
+        torch.autograd.backward([out, loss], [g_out, g_loss])
+        host_q.copy_(out.detach(), non_blocking=True)
+        host_i.copy_(inds, non_blocking=True)
         host_loss.copy_(loss.detach(), non_blocking=True)
+        dz.grad = None
+        for p in params:
+            p.grad = None
         torch.cuda.current_stream().synchronize()  # the user reads the loss (experiment.py:96 .item())
         return float(host_loss)
 
@@ -442,46 +682,64 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = rows_per_gpu * world * e2e_steps / (float(te) * 1e-3)
-    del host_z, dz
+    h2d = B * D * H * W * 4
+    d2h = B * D * H * W * 4 + B * C * H * W * 8 + 4
+    del host_z, host_q, host_i, dz
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------
-    peak, peak_src = peaks()
+    hbm_peak, tc_peak, peak_src = peaks()
     fb, bb = algorithmic_bytes_per_row(C, d, D)
     kernels = [
         {"kernel": "vq_fwd (argmin+gather+ST+loss)", "path": {1: "simt", 2: "tcgen05"}.get(fwd_path, "?"),
          "ms": fwd_ms, "alg_bytes": fb * rows_per_gpu, "gbs": fb * rows_per_gpu / (fwd_ms * 1e-3) / 1e9},
-        {"kernel": "vq_backward (grad_z + codebook scatter-add)", "ms": bwd_ms, "alg_bytes": bb * rows_per_gpu,
-         "gbs": bb * rows_per_gpu / (bwd_ms * 1e-3) / 1e9},
+        {"kernel": "vq_backward (grad_z + codebook scatter-add" + (" + fused all-reduce)" if world > 1 and getattr(comm, "fuses_backward", False) else ")"),
+         "ms": bwd_ms, "alg_bytes": bb * rows_per_gpu, "gbs": bb * rows_per_gpu / (bwd_ms * 1e-3) / 1e9},
     ]
-    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full capture
-    # of this very workload (profiles/r1_fwd_ws_b16384.md); only quoted for the profiled batch size
+    # DRAM traffic per launch: NOT measured by this run (it needs ncu); the figures come from the committed
+    # `ncu --set full` capture of this very workload and are quoted only for the profiled batch size
     ncu_traffic = {16384: (146883328 + 511268352, 717339648 + 497255936)}.get(B)
     for i, k in enumerate(kernels):
-        k["frac"] = k["gbs"] / peak
+        k["frac"] = k["gbs"] / hbm_peak
         k["traffic"] = ncu_traffic[i] if ncu_traffic else None
+        k["traffic_source"] = "ncu capture profiles/r1_fwd_ws_b16384.md (dram__bytes_read.sum + dram__bytes_write.sum)" if ncu_traffic else None
     dom = max(kernels, key=lambda k: k["ms"])
-    roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": dom["traffic"], "kernel": dom["kernel"], "peak_source": peak_src,
-                "alg_bytes_per_latent": {"fwd": fb, "bwd": bb}}
+    roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": dom["traffic"], "traffic_source": dom["traffic_source"], "kernel": dom["kernel"],
+                "peak_source": peak_src, "alg_bytes_per_latent": {"fwd": fb, "bwd": bb},
+                "reps_timed": reps}
 
+    subs = lat = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        subs, lat = sub_records(pkg, _lib, dev, hbm_peak, tc_peak)
     train = None
     if not args.no_train:
         train = bench_train(args, dev, world, rank, comm)
-    cpu = None
-    eager = None
+    eager = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        eager = torch_eager_gpu_baseline(dev, B)
+    clocks = sampler.stop() if sampler else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        parity = parity_report(m, dev)
         cpu = cpu_baseline()
-        eager = torch_eager_gpu_baseline(dev)
+    if parity is not None:
+        parity["near_tie_rows_per_benchmark_step"] = near_per_step
 
     if rank == 0:
+        fused = world > 1 and getattr(comm, "fuses_backward", False)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(B, world), collective=(type(comm).__name__ if comm is not None else "none")),
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * D * H * W * 4 * world,
-                        "d2h_bytes_per_step": 4 * world, "steps": e2e_steps},
-                "gpu_launches": (2 + (1 if world > 1 and not getattr(comm, "fuses_backward", False) else 0)) * args.steps,
-                "collective_check": collective_check, "roofline": roofline, "kernels": kernels, "clocks": clocks, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "train": train}
+                "config": dict(workload_config(B, world), collective=(type(comm).__name__ if comm is not None else "none"),
+                               schedule="one stream, program order: forward, backward" + (" (all-reduce fused in its last CTA)" if fused else (", all-reduce" if world > 1 else "")),
+                               numa=numa),
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+                        "what": "latents H2D from pinned memory; quantised output, int64 indices and loss D2H; forward + backward"},
+                "gpu_launches": (2 + (1 if world > 1 and not fused else 0)) * args.steps,
+                "collective_check": collective_check, "roofline": roofline, "kernels": kernels, "clocks": clocks,
+                "parity": parity, "sub_records": subs, "latency_at_config_batch": lat,
+                "cpu_baseline": cpu, "gpu_eager_baseline": eager, "train": train}
         emit(line)
     if world > 1:
         if comm is not None:
@@ -490,36 +748,41 @@ def main():
 
 
 def bench_train(args, dev, world, rank, comm):
-    """Second half of BASELINE.json's metric: MCQ-VAE (configs/mcq_vae.yaml) training images/s — conv
+    """Second half of BASELINE.json's metric: MCQ-VAE (configs/mcq_vae.yaml) training images/s -- conv
     encoder/decoder on stock cuDNN exactly like the reference, the quantiser on our kernels, Adam lr 5e-4
-    (mcq_vae.yaml:23); N>1: torch DDP for the model, batch-sharded."""
+    (mcq_vae.yaml:23); N>1: batch-sharded, one flat-gradient all-reduce per step.  At N=1 the same shell is also run with
+    the reference's stock-torch quantiser (EagerMCQ) on the same GPU, which isolates what the quantiser contributes."""
     import torch.distributed as dist
 
-    import ct_vae_b200 as pkg
     from ct_vae_b200.harness import GraphedTrainer, MCQVAEShell
 
     B = args.train_batch
+    steps, warm = max(20, args.steps), max(5, args.warmup)
+
+    def run(model):
+        trainer = GraphedTrainer(model, (B, 3, 64, 64), dev, lr=5e-4, world=world)
+        torch.manual_seed(1320 + rank)
+        x = torch.rand(B, 3, 64, 64, device=dev)  # Shapes3D images are in [0,1] after ToTensor (dataset.py:72-75)
+        for _ in range(warm):
+            trainer.step(x)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        n = max(steps, 30)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            trainer.step(x)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return trainer, float(t) / n
+
     torch.manual_seed(1320)
     model = MCQVAEShell(3, 128, 64, [64, 128, 256], 0.25, 64, 4).to(dev)
-    trainer = GraphedTrainer(model, (B, 3, 64, 64), dev, lr=5e-4, world=world)
-    torch.manual_seed(1320 + rank)
-    x = torch.rand(B, 3, 64, 64, device=dev)  # Shapes3D images are in [0,1] after ToTensor (dataset.py:72-75)
-    steps, warm = max(20, args.steps), max(5, args.warmup)
-    for _ in range(warm):
-        trainer.step(x)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        trainer.step(x)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t)
+    trainer, ms = run(model)
     # e2e: images from pinned host memory each step + loss read back to the host (experiment.py:96 .item())
     hx = torch.rand(B, 3, 64, 64).pin_memory()
     for _ in range(2):
@@ -534,13 +797,28 @@ def bench_train(args, dev, world, rank, comm):
     te = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    return {"metric": "mcq_vae_train_images_per_sec", "value": B * world * steps / (ms * 1e-3), "unit": "images/s",
-            "batch_per_gpu": B, "steps": steps, "ms_per_step": ms / steps,
-            "e2e": {"value": B * world * steps / (float(te) * 1e-3), "unit": "images/s",
-                    "h2d_bytes_per_step": B * 3 * 64 * 64 * 4 * world, "d2h_bytes_per_step": 4 * world},
-            "cuda_graph": trainer.graph is not None,
-            "model": "MCQVAEShell = layer structure of models/mcq_vae.py:142-317 (10.1 M params), cuDNN convs, "
-                     "ctvq quantiser, Adam lr 5e-4; step replayed from two CUDA graphs (fwd+bwd, Adam) with one eager NCCL all-reduce of the flat gradient between them for N>1"}
+    out = {"metric": "mcq_vae_train_images_per_sec", "value": B * world / (ms * 1e-3), "unit": "images/s",
+           "batch_per_gpu": B, "ms_per_step": ms,
+           "e2e": {"value": B * world * steps / (float(te) * 1e-3), "unit": "images/s",
+                   "h2d_bytes_per_step": B * 3 * 64 * 64 * 4 * world, "d2h_bytes_per_step": 4 * world},
+           "cuda_graph": trainer.graph is not None,
+           "model": "MCQVAEShell = layer structure of models/mcq_vae.py:142-317 (10.1 M params), cuDNN convs, "
+                    "ctvq quantiser, Adam lr 5e-4; step replayed from two CUDA graphs (fwd+bwd, Adam) with one eager NCCL all-reduce of the flat gradient between them for N>1"}
+    if world == 1:
+        try:
+            torch.manual_seed(1320)
+            base = MCQVAEShell(3, 128, 64, [64, 128, 256], 0.25, 64, 4)
+            base.vq_layer = EagerMCQ(64, 128, 4, 0.25)
+            base = base.to(dev)
+            tb, ms_b = run(base)
+            out["stock_quantiser_baseline"] = {"value": B / (ms_b * 1e-3), "unit": "images/s", "ms_per_step": ms_b,
+                                               "cuda_graph": tb.graph is not None,
+                                               "what": "same shell, same GPU, same CUDA-graph trainer; vq_layer = the reference's op "
+                                                       "sequence in stock torch (EagerMCQ)"}
+            out["speedup_vs_stock_quantiser"] = ms_b / ms
+        except Exception as e:
+            out["stock_quantiser_baseline"] = {"error": repr(e)[:200]}
+    return out
 
 
 if __name__ == "__main__":

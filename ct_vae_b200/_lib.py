@@ -38,6 +38,8 @@ _SIGNATURES = {
     "ctvq_nccl_comm_init": (_i, [ctypes.POINTER(_vp), _i, _i, _vp, _i]),
     "ctvq_nccl_comm_destroy": (_i, [_vp]),
     "ctvq_allreduce_codebook_grad": (_i, [_vp, _vp, _sz, _f, _i, _vp]),
+    "ctvq_debug_set_fast_trace": (None, [_vp]),
+    "ctvq_debug_set_tc_dump": (None, [_vp]),
     "ctvq_peer_buffer_bytes": (_sz, [_sz, _i]),
     "ctvq_peer_alloc": (_i, [ctypes.POINTER(_vp), _sz, _i, _i]),
     "ctvq_peer_free": (_i, [_vp, _i]),

@@ -452,20 +452,191 @@ int launch_tma(const BwdParams& p, cudaStream_t s) {
     kern<<<grid, kBT4, smem, s>>>(p, (int)nt);
     return (int)cudaGetLastError();
 }
+
+// Single full-width codebook with FEW codes and WIDE rows (configs/ct_mcq_vae.yaml: C=1, d=128, K=64, latents [B,128,8,8]).
+// Same skeleton as vq_bwd_tma_kernel (one image per tile, persistent CTA, g_out streamed by a cp.async.bulk ring), with
+// three changes that make a 128-channel tile fit and balance the two halves:
+//   * z is staged by 4-byte cp.async copies straight into the padded [D][TM+1] tile (no register prefetch: 128 channels
+//     per row would cost 64 registers per staging thread), TWO tiles ahead, double-buffered, issued by the gz warps (which
+//     have the lighter half of the work) and completed on an mbarrier (cp.async.mbarrier.arrive.noinc);
+//   * the JCH = D/32 "acc" warps (lane = channel, warp = 32-channel chunk of the shared [K,D] accumulator: race-free by
+//     ownership, plain read-modify-write -- fp32 shared atomics compile to a compare-and-swap loop, ATOMS.CAST.SPIN, on
+//     sm_100a) leave q - z IN PLACE of z, so the NGZ "gz" warps compute grad_z = g_out - coef_z (q - z) from shared memory only
+//     -- no index decode, no codebook copy padded for row-wise gathers.
+template <int D, int K, int HWT, int NST>
+__global__ void __launch_bounds__(256, 1) vq_bwd_c1_tma_kernel(const BwdParams p, const int ntiles) {
+    constexpr int TM = HWT;
+    constexpr int ZS = TM + 1;
+    constexpr int KD = K * D;
+    constexpr int JCH = D / 32;            // acc warps
+    constexpr int NGZ = 8 - JCH;           // gz warps
+    constexpr int NAT = JCH * 32, NGT = NGZ * 32;
+    constexpr int GOF = D * TM;            // floats per g_out stage
+    constexpr int kDiff = 1, kAcc = 3, kGz = 4;  // named barrier ids (kDiff + buf)
+    static_assert(D % 32 == 0 && JCH >= 1 && JCH <= 4 && TM == 64 && (D * TM) % NGT == 0, "shape");
+    extern __shared__ __align__(128) float smem[];
+    float* go_s = smem;                                        // [NST][D][TM]
+    int* idx_s = reinterpret_cast<int*>(go_s + NST * GOF);     // [2][TM]
+    float* zs = reinterpret_cast<float*>(idx_s + 2 * TM);      // [2][D][ZS]: z, then q - z in place
+    float* acc = zs + 2 * D * ZS;                              // [K][D]
+    float* es = acc + KD;                                      // [K][D]  (read with lanes along the channel only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(es + KD);     // full[NST], empty[NST], zfull[2]
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NST]), bar_zfull = smem_u32(&bars[2 * NST]);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, NGZ); }
+        for (int i = 0; i < 2; ++i) mbar_init(bar_zfull + 8 * i, NGT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < KD; i += 256) { acc[i] = 0.0f; es[i] = __ldg(p.E[0] + i); }
+    const float gl = __ldg(p.g_loss);
+    const double nd = (double)p.N * (double)D;
+    const float coef_e = (float)(2.0 / nd) * gl;
+    const float coef_z = (float)(2.0 * (double)p.beta / nd) * gl;
+    __syncthreads();
+    const int niter = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool has_go = p.g_out != nullptr;
+
+    if (warp < JCH) {
+        // =========================== acc warps: codebook-gradient accumulation, q - z left in place ===========================
+        auto issue_go = [&](int it) {  // thread 0: stream image it's g_out block into ring slot it % NST
+            const int st = it % NST;
+            if (it >= NST) mbar_wait(bar_empty + 8 * st, (uint32_t)((it / NST) - 1) & 1u);
+            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+            mbar_expect_tx(bar_full + 8 * st, GOF * 4u);
+            bulk_g2s(smem_u32(go_s + st * GOF), p.g_out + (size_t)b * GOF, GOF * 4u, bar_full + 8 * st);
+        };
+        if (tid == 0 && has_go)
+            for (int it = 0; it < NST - 1 && it < niter; ++it) issue_go(it);
+        for (int it = 0; it < niter; ++it) {
+            const int buf = it & 1;
+            if (tid == 0 && has_go && it + NST - 1 < niter) issue_go(it + NST - 1);
+            if (tid < TM) {  // this tile's indices (range-checked like every consumer of caller-supplied indices)
+                const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+                long long kk = __ldg(p.idx + (size_t)b * HWT + tid);
+                if (kk < 0 || kk >= K) { atomicOr(p.err, 1u); kk = kk < 0 ? 0 : K - 1; }
+                idx_s[buf * TM + tid] = (int)kk;
+            }
+            mbar_wait(bar_zfull + 8 * buf, (uint32_t)(it >> 1) & 1u);  // the gz warps' cp.async copies of this tile have landed
+            named_sync(kAcc, NAT);                                      // ... and the indices are published
+            float* zb = zs + buf * D * ZS + (warp * 32 + lane) * ZS;    // this lane's channel column
+            const int* ks = idx_s + buf * TM;
+            float* ac = acc + warp * 32 + lane;
+            const float* ec = es + warp * 32 + lane;
+            auto diffs = [&](const int4& kk, int r) {
+                return make_float4(__fsub_rn(ec[kk.x * D], zb[r]), __fsub_rn(ec[kk.y * D], zb[r + 1]),
+                                   __fsub_rn(ec[kk.z * D], zb[r + 2]), __fsub_rn(ec[kk.w * D], zb[r + 3]));
+            };
+            // software pipeline, two row-groups ahead (as in vq_bwd_tma_kernel): loads of groups g+1, g+2 fly under the
+            // read-modify-write of group g; four rows update four DIFFERENT words unless two of them chose the same code
+            constexpr int NG = TM / 4;
+            int4 kA = *reinterpret_cast<const int4*>(ks), kB = *reinterpret_cast<const int4*>(ks + 4);
+            float4 dA = diffs(kA, 0), dB = diffs(kB, 4);
+#pragma unroll 4
+            for (int g = 0; g < NG; ++g) {
+                int4 kC = kB;
+                float4 dC = dB;
+                if (g + 2 < NG) {
+                    kC = *reinterpret_cast<const int4*>(ks + (g + 2) * 4);
+                    dC = diffs(kC, (g + 2) * 4);
+                }
+                const bool distinct = kA.x != kA.y && kA.x != kA.z && kA.x != kA.w && kA.y != kA.z && kA.y != kA.w && kA.z != kA.w;
+                if (distinct) {
+                    const float a0 = ac[kA.x * D], a1 = ac[kA.y * D], a2 = ac[kA.z * D], a3 = ac[kA.w * D];
+                    ac[kA.x * D] = a0 + dA.x; ac[kA.y * D] = a1 + dA.y; ac[kA.z * D] = a2 + dA.z; ac[kA.w * D] = a3 + dA.w;
+                } else {
+                    ac[kA.x * D] += dA.x; ac[kA.y * D] += dA.y; ac[kA.z * D] += dA.z; ac[kA.w * D] += dA.w;
+                }
+                zb[g * 4] = dA.x; zb[g * 4 + 1] = dA.y; zb[g * 4 + 2] = dA.z; zb[g * 4 + 3] = dA.w;  // q - z for the gz warps
+                kA = kB; dA = dB; kB = kC; dB = dC;
+            }
+            named_arrive(kDiff + buf, 256);                // this tile's differences are in place
+        }
+    } else {
+        // =========================== gz warps: z staging two tiles ahead; grad_z = g_out - coef_z (q - z) ========================
+        const int gw = warp - JCH, gt = tid - NAT;
+        const int hsel = lane >> 4;              // half-warp: which channel of the pair
+        const int m = (lane & 15) * 4;           // rows m..m+3
+        constexpr int CPT = D * TM / NGT;        // 4-byte copies per thread per tile
+        auto stage = [&](int it) {               // tile it -> buffer it & 1 (asynchronous; completion arrives on zfull[buf])
+            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const int buf = it & 1;
+            const float* src = p.z + (size_t)b * D * HWT;
+            float* dst = zs + buf * D * ZS;
+#pragma unroll 8
+            for (int i = 0; i < CPT; ++i) {
+                const int e = i * NGT + gt;      // element of the [D][TM] image block: coalesced along H*W
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + (e / TM) * ZS + (e % TM))), "l"(src + e) : "memory");
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_zfull + 8 * buf) : "memory");
+        };
+        for (int it = 0; it < 2 && it < niter; ++it) stage(it);
+        for (int it = 0; it < niter; ++it) {
+            const int buf = it & 1, st = it % NST;
+            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const float* zb = zs + buf * D * ZS;
+            const float* gos = go_s + st * GOF;
+            float* gz_row = p.gz + (size_t)b * D * HWT + m;
+            named_sync(kDiff + buf, 256);
+            if (has_go) mbar_wait(bar_full + 8 * st, (uint32_t)(it / NST) & 1u);
+#pragma unroll 4
+            for (int ch = 2 * gw + hsel; ch < D; ch += 2 * NGZ) {
+                const float d0 = zb[ch * ZS + m], d1 = zb[ch * ZS + m + 1], d2 = zb[ch * ZS + m + 2], d3 = zb[ch * ZS + m + 3];
+                float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_go) go = *reinterpret_cast<const float4*>(gos + ch * TM + m);
+                *reinterpret_cast<float4*>(gz_row + (size_t)ch * HWT) =
+                    make_float4(go.x - coef_z * d0, go.y - coef_z * d1, go.z - coef_z * d2, go.w - coef_z * d3);
+            }
+            __syncwarp();
+            if (lane == 0 && has_go) mbar_arrive(bar_empty + 8 * st);  // ring slot may be refilled
+            if (it + 2 < niter) {
+                named_sync(kGz, NGT);            // every gz warp is done reading this buffer
+                stage(it + 2);                   // ... which tile it+2 re-uses
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < KD; i += 256) {
+        const float v = acc[i];
+        if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
+    }
+    peer_tail(p.peer, p.gE);
+}
+
+template <int D, int K, int HWT, int NST>
+int launch_c1_tma(const BwdParams& p, cudaStream_t s) {
+    constexpr size_t smem = sizeof(float) * ((size_t)NST * D * HWT + 2 * (size_t)HWT + 2 * (size_t)D * (HWT + 1) + 2 * (size_t)K * D) + (2 * NST + 2) * 8;
+    static_assert(smem <= 227 * 1024, "shared memory");
+    if (p.N % HWT != 0) return CTVQ_E_UNSUPPORTED;
+    const long long nt = p.N / HWT;  // one image per tile
+    if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
+    int grid = sm_count();
+    if (grid > nt) grid = (int)nt;
+    auto kern = vq_bwd_c1_tma_kernel<D, K, HWT, NST>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, 256, smem, s>>>(p, (int)nt);
+    return (int)cudaGetLastError();
+}
 }  // namespace
 
 int launch_backward_fast(const BwdParams& p, cudaStream_t s) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(p.gz) & 15) == 0) &&
                          (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 15) == 0);
     if (!aligned) return CTVQ_E_UNSUPPORTED;
+    static const bool no_tma = getenv("CTVQ_BWD_NO_TMA") != nullptr;  // A/B switch, read once per process
     // configs/mcq_vae.yaml: C=4, d=32, K=64, latents [B,128,8,8], overlapping slices
     if (p.d == 32 && p.C == 4 && p.K == 64 && p.HW == 64 && p.Dtot == 128 && p.cs == 1) {
         const bool go_ok = p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0;
-        if (go_ok && p.N >= (long long)sm_count() * 64 * 4 && !getenv("CTVQ_BWD_NO_TMA")) return launch_tma<32, 4, 64, 64, 128, 1>(p, s);
+        if (go_ok && p.N >= (long long)sm_count() * 64 * 4 && !no_tma) return launch_tma<32, 4, 64, 64, 128, 1>(p, s);
         return launch<32, 4, 64, 64, 128, 1, 2>(p, s);
     }
     // configs/ct_mcq_vae.yaml: C=1, d=128, K=64, latents [B,128,8,8]
-    if (p.d == 128 && p.C == 1 && p.K == 64 && p.HW == 64 && p.Dtot == 128) return launch<128, 1, 64, 64, 128, 1, 1>(p, s);
+    if (p.d == 128 && p.C == 1 && p.K == 64 && p.HW == 64 && p.Dtot == 128) {
+        const bool ok = (reinterpret_cast<uintptr_t>(p.z) & 3) == 0 && (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0);
+        if (ok && p.N >= (long long)sm_count() * 64 * 2 && !no_tma) return launch_c1_tma<128, 64, 64, 2>(p, s);
+        return launch<128, 1, 64, 64, 128, 1, 1>(p, s);
+    }
     return CTVQ_E_UNSUPPORTED;
 }
 

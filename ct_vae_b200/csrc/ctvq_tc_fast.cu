@@ -471,6 +471,10 @@ int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
         // -- the L1/shared data pipe, not latency, is the limiter, so more warps only add contention
         return launch_fast<32, 64, 64, 4, 1, 5, 4>(p, s);
     }
+    // neighbours of that shape: the same model on 128x128 images (H*W = 256), and two codebooks instead of four
+    if (p.d == 32 && p.cs == 1 && p.C == 4 && p.HW == 256) return launch_fast<32, 64, 256, 4, 1, 5, 4>(p, s);
+    if (p.d == 32 && p.cs == 1 && p.C == 2 && p.HW == 64) return launch_fast<32, 64, 64, 2, 1, 5, 4>(p, s);
+    if (p.d == 32 && p.cs == 1 && p.C == 2 && p.HW == 256) return launch_fast<32, 64, 256, 2, 1, 5, 4>(p, s);
     return CTVQ_E_UNSUPPORTED;
 }
 

@@ -32,11 +32,12 @@ using namespace tc;
 namespace {
 
 constexpr int kEW = 16;                  // epilogue warps
-constexpr int kRT = 32 * kEW + 32;       // + the producer warp
+constexpr int kRT = 32 * kEW + 64;       // + the MMA-issue warp and the TMA-issue warp (one lane each)
 
 struct ResParams {
     QuantParams q;
     int ntiles;
+    unsigned hw_mul, hw_shift;   // n / HW for 32-bit n as (((n - t) >> 1) + t) >> hw_shift, t = umulhi(n, hw_mul)
     const float* ee;             // [NK] exact |e_k|^2 (+inf for padded codes), written by res_prep_kernel
     const unsigned* emax_bits;   // max |e_k|^2 as float bits (NaN / inf poison the bound)
 };
@@ -50,12 +51,20 @@ __device__ __forceinline__ void tma_load_2d_r(uint32_t dst, const CUtensorMap* m
 __device__ __forceinline__ void or_if_ge_r(unsigned& m, float a, float lim, unsigned bit) {
     asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(a), "f"(lim), "r"(bit));
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {  // global -> L2 only
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ unsigned fast_div(unsigned n, unsigned mul, unsigned shift) {
+    const unsigned t = __umulhi(n, mul);
+    return (((n - t) >> 1) + t) >> shift;
+}
 __device__ __forceinline__ float sqrt_approx_r(float x) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
+constexpr int kL2Ahead = 2;  // tiles requested into L2 ahead of their shared-memory load
 constexpr int kCap = 128;  // pairs per (tile parity, lane quarter) list: one per thread of the four slice warps
 
 // (distance, code) as ONE 64-bit key whose unsigned order is torch.argmin's: NaN first, then ascending distance
@@ -88,22 +97,25 @@ __global__ void res_prep_kernel(const float* __restrict__ E, int K, int D, int N
     ee[k] = a;
 }
 
-// D: channels (32 / 64); NH: 256-code units per tile (K <= 256*NH); NSTAGE: slab ring depth
-template <int D, int NH, int NSTAGE>
+// D: channels (32 / 64 / 128); NKU: codes per unit = accumulator columns per buffer (256, or 64 for small codebooks);
+// NH: units per tile (K <= NKU*NH); NSTAGE: slab ring depth
+template <int D, int NKU, int NH, int NSTAGE>
 __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P, const __grid_constant__ Maps maps,
                                                                const __grid_constant__ CUtensorMap emap) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const QuantParams& p = P.q;
     const int K = p.K, HW = p.HW;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NK = NH * 256;
+    constexpr int NK = NH * NKU;
+    constexpr int SL = NKU / 4;                      // columns of one warp's slice of a unit (64 or 16)
     constexpr int KB = D / 32;                       // 128-byte K-blocks of the codebook operand
     constexpr int CH = D / 4;                        // channels of a thread's gather slice
     constexpr uint32_t kBlk = (uint32_t)D * 128u;    // one 32-row block of a slab: [D][128 B]
     constexpr uint32_t kStage = 4u * kBlk;
     constexpr uint32_t kBbytes = (uint32_t)KB * NK * 128u;
-    constexpr uint32_t kXunit = 8u * 1024u;          // extra-K-group operand of one unit: [8 groups of 32 codes][8 k][128 B]
-    static_assert(D == 32 || D == 64, "channel slices of 8 / 16 per warp");
+    constexpr uint32_t kXunit = (uint32_t)(NKU / 32) * 1024u;  // extra-K-group operand of one unit: [NKU/32 groups of 32 codes][8 k][128 B]
+    static_assert(D == 32 || D == 64 || D == 128, "channel slices of 8 / 16 / 32 per warp");
+    static_assert(NKU == 256 || NKU == 64, "slices of 64 or 16 columns");
     static_assert(NSTAGE >= 2, "ring");
     uint8_t* a_s = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_s = a_s + (size_t)NSTAGE * kStage;
@@ -133,20 +145,27 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
     __syncthreads();  // barriers initialised before the first TMA may signal them
 
     const int niter = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const bool producer = (tid == 32 * kEW);
-    auto issue_tma = [&](int it) {  // producer only: TMA-load the tile of iteration `it` into its ring slot
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int seg = tile / p.tiles_per_seg;
-        const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
+    const bool producer = (tid == 32 * (kEW + 1));  // the TMA-issue lane
+    const unsigned tps = (unsigned)p.tiles_per_seg;
+    auto tile_pos = [&](int it, int& seg, unsigned& row0) {  // tile of iteration `it` -> (segment, first row); N < 2^31 rows per segment
+        const unsigned tile = blockIdx.x + (unsigned)it * gridDim.x;
+        seg = (p.n_seg == 1) ? 0 : (int)(tile / tps);
+        row0 = (tile - (unsigned)seg * tps) * (unsigned)kTM;
+    };
+    auto issue_tma = [&](int it, bool l2_only) {  // TMA lane: load the tile of iteration `it` into its ring slot / into L2
+        int seg;
+        unsigned row0;
+        tile_pos(it, seg, row0);
         const int st = it % NSTAGE;
         int nblk = 0;
 #pragma unroll
-        for (int mb = 0; mb < 4; ++mb) nblk += (row0 + 32 * mb < p.N) ? 1 : 0;
-        mbar_expect_tx(bar_full0 + 8 * st, (uint32_t)nblk * kBlk);
+        for (int mb = 0; mb < 4; ++mb) nblk += ((long long)row0 + 32 * mb < p.N) ? 1 : 0;
+        if (!l2_only) mbar_expect_tx(bar_full0 + 8 * st, (uint32_t)nblk * kBlk);
         for (int mb = 0; mb < nblk; ++mb) {
-            const long long nb = row0 + 32 * mb;
-            const long long bb = nb / HW;
-            tma_load_3d(a_base + st * kStage + mb * kBlk, &maps.m[seg], bar_full0 + 8 * st, (int)(nb - bb * HW), 0, (int)bb);
+            const unsigned nb = row0 + 32u * mb;
+            const unsigned bb = fast_div(nb, P.hw_mul, P.hw_shift);
+            if (l2_only) tma_prefetch_3d(&maps.m[seg], (int)(nb - bb * (unsigned)HW), 0, (int)bb);
+            else tma_load_3d(a_base + st * kStage + mb * kBlk, &maps.m[seg], bar_full0 + 8 * st, (int)(nb - bb * (unsigned)HW), 0, (int)bb);
         }
     };
     if (producer) {
@@ -155,7 +174,8 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
         for (int kb = 0; kb < KB; ++kb)
             for (int i = 0; i < NK / 64; ++i)
                 tma_load_2d_r(b_base + (uint32_t)kb * NK * 128u + (uint32_t)i * 8192u, &emap, bar_bfull, kb * 32, i * 64);
-        for (int it = 0; it < NSTAGE && it < niter; ++it) issue_tma(it);
+        for (int it = 0; it < NSTAGE && it < niter; ++it) issue_tma(it, false);
+        for (int it = NSTAGE; it < NSTAGE + kL2Ahead && it < niter; ++it) issue_tma(it, true);
     }
     // extra K-group operands: x[unit][code][k] = -|e|^2/2 as three tf32-exact terms (k = 0..2), zero for k = 3..7
     for (int n = tid; n < NK; n += kRT) {
@@ -168,8 +188,8 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
             t[1] = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
             t[2] = __uint_as_float(__float_as_uint(r1 - t[1]) & 0xFFFFE000u);
         }
-        const int m = n & 255;
-        uint8_t* blk = x_s + (size_t)(n >> 8) * kXunit + (size_t)(m >> 5) * 1024;
+        const int m = n % NKU;
+        uint8_t* blk = x_s + (size_t)(n / NKU) * kXunit + (size_t)(m >> 5) * 1024;
 #pragma unroll
         for (int j = 0; j < 8; ++j) *reinterpret_cast<float*>(blk + a_off(m & 31, j)) = t[j];
     }
@@ -184,13 +204,26 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
 
     float lsum = 0.0f;
     unsigned nnear = 0u;  // near-tie rows seen by this thread (include/ctvq.h)
-    if (warp == kEW) {
-        // =============================== producer: slab TMA ring + MMA groups =========================================
+    if (warp == kEW + 1) {
+        // =============================== TMA lane: slab ring, kept kL2Ahead tiles ahead in L2 ========================
+        // A slab can only be re-filled once every epilogue warp has scored its last candidate from it, which leaves less
+        // than a tile time of lookahead with the 2 stages that fit beside a 128 KB codebook -- not enough to cover HBM
+        // latency.  So every tile is ALSO requested into L2 kL2Ahead tiles early (cp.async.bulk.prefetch.tensor): the
+        // late shared-memory load then completes at L2 latency.  HBM traffic is unchanged (one read per slab).
         if (lane == 0) {
-            const uint32_t idesc = instr_desc_tf32(256);
+            for (int nx = NSTAGE; nx < niter; ++nx) {
+                const int prev = nx - NSTAGE;
+                if (nx + kL2Ahead < niter) issue_tma(nx + kL2Ahead, true);
+                mbar_wait_fast(bar_empty0 + 8 * (prev % NSTAGE), (uint32_t)(prev / NSTAGE) & 1u);
+                issue_tma(nx, false);
+            }
+        }
+    } else if (warp == kEW) {
+        // =============================== MMA lane ====================================================================
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_tf32(NKU);
             const uint32_t idesc_x = idesc | (1u << 16);  // extra K-group: B operand MN-major as well
             mbar_wait_fast(bar_bfull, 0u);
-            int tma_next = NSTAGE < niter ? NSTAGE : niter;
             for (int it = 0; it < niter; ++it) {
                 const int st = it % NSTAGE;
                 const uint32_t stage_u32 = a_base + st * kStage;
@@ -200,11 +233,11 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
                     const int u = it * NH + h, buf = u & 1;
                     if (u >= 2) mbar_wait_fast(bar_tfree + 8 * buf, (uint32_t)((u >> 1) - 1) & 1u);
                     tc_fence_after();
-                    const uint32_t dcol = tmem_base + buf * 256;
+                    const uint32_t dcol = tmem_base + buf * NKU;
 #pragma unroll
                     for (int s = 0; s < D / 8; ++s) {
                         const uint64_t ad = smem_desc(stage_u32 + (uint32_t)s * 1024u, kBlk, 512u, 1u);
-                        const uint64_t bd = smem_desc(b_base + (uint32_t)(s >> 2) * NK * 128u + (uint32_t)h * 256u * 128u + (s & 3) * 32u,
+                        const uint64_t bd = smem_desc(b_base + (uint32_t)(s >> 2) * NK * 128u + (uint32_t)h * NKU * 128u + (s & 3) * 32u,
                                                       16u, 1024u, 2u);
                         umma_tf32(dcol, ad, bd, idesc, s > 0 ? 1u : 0u);
                     }
@@ -214,12 +247,6 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
                     umma_commit(bar_m + 8 * buf);
                 }
                 umma_commit(bar_empty0 + 8 * st);  // every MMA that reads this slab has been issued before this commit
-                while (tma_next < niter && tma_next <= it + NSTAGE - 1) {
-                    const int prev = tma_next - NSTAGE;
-                    mbar_wait_fast(bar_empty0 + 8 * (prev % NSTAGE), (uint32_t)(prev / NSTAGE) & 1u);
-                    issue_tma(tma_next);
-                    ++tma_next;
-                }
             }
         }
     } else {
@@ -252,13 +279,13 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
             return dist_f32(zz, __ldg(P.ee + k), dot);
         };
         for (int it = 0; it < niter; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int seg = tile / p.tiles_per_seg;
-            const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
-            const long long n = row0 + r;
-            const bool valid = n < p.N;  // uniform over the four warps of a quarter (N is a multiple of 32)
-            const long long b = n / HW;
-            const int hw = (int)(n - b * HW);
+            int seg;
+            unsigned row0;
+            tile_pos(it, seg, row0);
+            const unsigned n = row0 + (unsigned)r;
+            const bool valid = (long long)n < p.N;  // uniform over the four warps of a quarter (N is a multiple of 32)
+            const unsigned b = fast_div(n, P.hw_mul, P.hw_shift);
+            const int hw = (int)(n - b * (unsigned)HW);
             const int st = it % NSTAGE, par = it & 1;
             unsigned long long* keyp = key_s + par * 128;
             unsigned* nearp = near_s + par * 128;
@@ -287,18 +314,19 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
                 const int u = it * NH + h, buf = u & 1;
                 mbar_wait_fast(bar_m + 8 * buf, (uint32_t)(u >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + s * 64;
-                uint32_t a[32];
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NKU + s * SL;
+                constexpr int LW = SL >= 32 ? 32 : SL;   // columns per TMEM load
+                uint32_t a[LW];
                 float pmh = -CUDART_INF_F;
                 if (valid) {
-                    // ---- pass 1: maximum of this slice's 64 approximate scores --------------------------------------
+                    // ---- pass 1: maximum of this slice's SL approximate scores --------------------------------------
                     float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        tmem_ld32_issue(trow + 32 * hh, a);
-                        tmem_ld32_wait(a);
+                    for (int hh = 0; hh < SL / LW; ++hh) {
+                        tmem_ld_issue(trow + LW * hh, a);
+                        tmem_ld_wait(a);
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
+                        for (int i = 0; i < LW; i += 4) {
                             m0 = fmaxf(m0, __uint_as_float(a[i])); m1 = fmaxf(m1, __uint_as_float(a[i + 1]));
                             m2 = fmaxf(m2, __uint_as_float(a[i + 2])); m3 = fmaxf(m3, __uint_as_float(a[i + 3]));
                         }
@@ -324,15 +352,18 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
                     const float lim = run - 0.5f * thr;  // running maximum: a superset of the final survivor set
                     // ---- pass 2: survivors as a bitmask (both halves re-read from TMEM: nothing lives across the barrier) --
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        tmem_ld32_issue(trow + 32 * hh, a);
-                        tmem_ld32_wait(a);
+                    for (int hh = 0; hh < SL / LW; ++hh) {
+                        tmem_ld_issue(trow + LW * hh, a);
+                        tmem_ld_wait(a);
                         unsigned mk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) or_if_ge_r(mk[i & 3], __uint_as_float(a[i]), lim, 1u << i);
+                        for (int i = 0; i < LW; ++i) or_if_ge_r(mk[i & 3], __uint_as_float(a[i]), lim, 1u << i);
                         const unsigned m = (mk[0] | mk[1]) | (mk[2] | mk[3]);
                         if (hh == 0) mlo[h] = m; else mhi[h] = m;
                     }
+                    // (an fma-pipe form of this pass -- t = sat((s - lim') * 2^80), bits summed in fp32 accumulators, two
+                    // immediate-form FFMAs per score -- was measured SLOWER: 0.275 vs 0.248 ms at K=512, 1 M rows; the kernel
+                    // is bound by its barrier / latency structure at 4 warps per scheduler, not by the alu pipe)
                 }
                 pm[h] = pmh;
                 tc_fence_before();
@@ -360,8 +391,8 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
 #pragma unroll 1
                     for (int h = 0; h < NH; ++h)
 #pragma unroll 1
-                        for (int i = 0; i < 64; ++i) {
-                            const int k = h * 256 + s * 64 + i;
+                        for (int i = 0; i < SL; ++i) {
+                            const int k = h * NKU + s * SL + i;
                             if (k >= K) break;
                             float zz;
                             const float dist = exact_dist(zblk, lane, k, zz);
@@ -372,8 +403,8 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
                         int k = 0;
 #pragma unroll
                         for (int h = 0; h < NH; ++h) {
-                            if (mlo[h]) k = h * 256 + s * 64 + __ffs(mlo[h]) - 1;
-                            if (mhi[h]) k = h * 256 + s * 64 + 32 + __ffs(mhi[h]) - 1;
+                            if (mlo[h]) k = h * NKU + s * SL + __ffs(mlo[h]) - 1;
+                            if (mhi[h]) k = h * NKU + s * SL + 32 + __ffs(mhi[h]) - 1;
                         }
                         keyp[r] = (unsigned long long)(unsigned)k;
                     } else {
@@ -387,7 +418,7 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
                                 while (mk) {
                                     const int i = __ffsll((long long)mk) - 1;
                                     mk &= mk - 1;
-                                    listp[e++] = ((unsigned)lane << 16) | (unsigned)(h * 256 + s * 64 + i);
+                                    listp[e++] = ((unsigned)lane << 16) | (unsigned)(h * NKU + s * SL + i);
                                 }
                             }
                         } else {
@@ -398,7 +429,7 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
                             for (int h = 0; h < NH; ++h) {
                                 unsigned long long mk = ((unsigned long long)mhi[h] << 32) | mlo[h];
                                 while (mk) {
-                                    const int k = h * 256 + s * 64 + __ffsll((long long)mk) - 1;
+                                    const int k = h * NKU + s * SL + __ffsll((long long)mk) - 1;
                                     mk &= mk - 1;
                                     float zz;
                                     const float dist = exact_dist(zblk, lane, k, zz);
@@ -515,15 +546,15 @@ int make_map_codebook(CUtensorMap* m, const float* base, uint64_t cols, uint64_t
     return r == CUDA_SUCCESS ? CTVQ_OK : CTVQ_E_UNSUPPORTED;
 }
 
-template <int D, int NH, int NSTAGE>
+template <int D, int NKU, int NH, int NSTAGE>
 constexpr size_t res_smem() {
-    return (size_t)NSTAGE * 4 * D * 128 + (size_t)(D / 32) * NH * 256 * 128 + (size_t)NH * 8192 + 4096 +
+    return (size_t)NSTAGE * 4 * D * 128 + (size_t)(D / 32) * NH * NKU * 128 + (size_t)NH * (NKU / 32) * 1024 + 4096 +
            sizeof(float) * (2 * 4 * 128 + 4 * 128) + 2 * 128 * 8 + 2 * 128 * 4 + (2 * 4 * kCap + 8) * 4 + (2 * NSTAGE + 5) * 8 + 16 + 1024;
 }
 
-template <int D, int NH, int NSTAGE>
+template <int D, int NKU, int NH, int NSTAGE>
 int launch_res(const QuantParams& p0, cudaStream_t s) {
-    constexpr int NK = NH * 256;
+    constexpr int NK = NH * NKU;
     // scratch: [emax bits, pad to 256 B][ee: NK floats]
     const size_t need = 256 + (size_t)NK * 4;
     if (!p0.scratch || p0.scratch_bytes < need || (reinterpret_cast<uintptr_t>(p0.scratch) & 255)) return CTVQ_E_UNSUPPORTED;
@@ -535,6 +566,12 @@ int launch_res(const QuantParams& p0, cudaStream_t s) {
     P.ntiles = P.q.tiles_per_seg * p0.n_seg;
     P.ee = ee;
     P.emax_bits = emax_bits;
+    {   // n / HW by multiply-shift (HW >= 32 here): l = ceil(log2 HW), mul = floor(2^32 (2^l - HW) / HW) + 1
+        unsigned l = 0;
+        while ((1u << l) < (unsigned)p0.HW) ++l;
+        P.hw_mul = (unsigned)((((unsigned long long)1 << 32) * ((1ull << l) - (unsigned)p0.HW)) / (unsigned)p0.HW + 1);
+        P.hw_shift = l - 1;
+    }
     Maps maps;
     if (make_maps(p0, maps, D) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
     CUtensorMap emap;
@@ -542,9 +579,9 @@ int launch_res(const QuantParams& p0, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(emax_bits, 0, 4, s);
     if (e != cudaSuccess) return (int)e;
     res_prep_kernel<<<(NK + 255) / 256, 256, 0, s>>>(p0.E[0], p0.K, D, NK, ee, emax_bits);
-    constexpr size_t smem = res_smem<D, NH, NSTAGE>();
+    constexpr size_t smem = res_smem<D, NKU, NH, NSTAGE>();
     static_assert(smem <= 227 * 1024, "one CTA per SM");
-    auto kern = vq_fwd_tc_res_kernel<D, NH, NSTAGE>;
+    auto kern = vq_fwd_tc_res_kernel<D, NKU, NH, NSTAGE>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int grid = sm_count();
@@ -553,26 +590,40 @@ int launch_res(const QuantParams& p0, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
+// (NKU, NH) for a shape, 0 when the kernel does not cover it
+static void res_plan(int d, int K, int& nku, int& nh) {
+    nku = nh = 0;
+    if (K <= 64 && (d == 64 || d == 128)) { nku = 64; nh = 1; return; }
+    const int units = (K + 255) / 256;
+    if (d == 64 && units <= 2) { nku = 256; nh = units; }
+    else if (d == 32 && units <= 4) { nku = 256; nh = units == 3 ? 4 : units; }
+}
+
 }  // namespace
 
 bool res_supported(const QuantParams& p) {
     if (p.C != 1 || p.HW % 32 != 0 || p.d != p.Dtot) return false;
-    if (!((p.d == 64 && p.K <= 512) || (p.d == 32 && p.K <= 1024))) return false;
+    int nku, nh;
+    res_plan(p.d, p.K, nku, nh);
+    if (!nku) return false;
+    if (p.N >= (1ll << 31) - 256 || p.HW > (1 << 20)) return false;  // 32-bit row arithmetic inside the kernel
     for (int sg = 0; sg < p.n_seg; ++sg)
         if (reinterpret_cast<uintptr_t>(p.z[sg]) & 15) return false;
     if (reinterpret_cast<uintptr_t>(p.E[0]) & 15) return false;
-    const size_t need = 256 + (size_t)((p.K + 255) / 256) * 256 * 4;
+    const size_t need = 256 + (size_t)nku * nh * 4;
     if (!p.scratch || p.scratch_bytes < need || (reinterpret_cast<uintptr_t>(p.scratch) & 255)) return false;
     return encode_fn() != nullptr;
 }
 
 int launch_forward_tc_res(const QuantParams& p, cudaStream_t s) {
     if (!res_supported(p)) return CTVQ_E_UNSUPPORTED;
-    const int nh = (p.K + 255) / 256;
-    if (p.d == 64) return nh == 1 ? launch_res<64, 1, 3>(p, s) : launch_res<64, 2, 2>(p, s);
-    if (nh == 1) return launch_res<32, 1, 4>(p, s);
-    if (nh == 2) return launch_res<32, 2, 4>(p, s);
-    return launch_res<32, 4, 3>(p, s);
+    int nku, nh;
+    res_plan(p.d, p.K, nku, nh);
+    if (nku == 64) return p.d == 128 ? launch_res<128, 64, 1, 2>(p, s) : launch_res<64, 64, 1, 4>(p, s);
+    if (p.d == 64) return nh == 1 ? launch_res<64, 256, 1, 3>(p, s) : launch_res<64, 256, 2, 2>(p, s);
+    if (nh == 1) return launch_res<32, 256, 1, 4>(p, s);
+    if (nh == 2) return launch_res<32, 256, 2, 4>(p, s);
+    return launch_res<32, 256, 4, 3>(p, s);
 }
 
 }  // namespace ctvq

@@ -7,8 +7,12 @@
  *
  * Conventions
  *   - extern "C", plain pointers and sizes; no torch types.  All data pointers are DEVICE pointers to
- *     caller-owned memory on `device`; the library allocates nothing and keeps no global mutable state
- *     (re-entrant; the caller passes a zero-initialised workspace per stream, ctvq_workspace_bytes()).
+ *     caller-owned memory on `device`; the compute entry points allocate nothing and are re-entrant (the caller
+ *     passes a zero-initialised workspace per stream, ctvq_workspace_bytes()).  PROCESS-GLOBAL state, all of it
+ *     set-once or test-only: the kernel-path override (ctvq_set_path: one atomic int, for tests and A/B runs), the
+ *     dlopen()ed NCCL function table (ctvq_nccl_load), the cached SM count per device, function attributes
+ *     (cudaFuncSetAttribute), the A/B environment switches CTVQ_BWD_NO_TMA / CTVQ_PEER_TIMEOUT_MS (read once), and
+ *     the two debug hooks at the end of this header.  ctvq_last_path() is per host thread.
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised (CUDA-graph safe).
  *   - return: 0 = OK, <0 = bad argument / unsupported shape (CTVQ_E_*), >0 = a cudaError_t.
  *     ctvq_strerror() renders either.
@@ -64,8 +68,8 @@ size_t ctvq_workspace_bytes(int C, int K, int d);
  * call copies the word to the host and clears it; it SYNCHRONISES `stream`.  *err_out != 0 -> the caller raises. */
 int ctvq_read_and_clear_err(void* workspace, size_t ws_bytes, unsigned* err_out_host, int device, void* stream);
 
-/* Force a kernel path for subsequent calls on this thread's library handle (tests/bench); AUTO picks
- * by shape.  Returns the previous value. */
+/* Force a kernel path for subsequent calls of the WHOLE PROCESS (one atomic int; tests / A-B runs only -- production code
+ * leaves it at AUTO, which picks by shape).  Returns the previous value. */
 int ctvq_set_path(int path);
 /* Which path the last ctvq_argmin/ctvq_forward call on this host thread dispatched to. */
 int ctvq_last_path(void);
@@ -191,6 +195,12 @@ int ctvq_backward_allreduce(const void* z, const void* const* codebooks, const i
                             int dtype, float beta, void* gz_out, float* gE_local, void* const* peer_bufs, int world,
                             int rank, size_t count_max, unsigned epoch, float scale, float* gE_reduced_out,
                             void* workspace, size_t ws_bytes, int device, void* stream);
+
+/* Debug hooks (development aids, not part of the product surface; both are process-global pointers, null = off):
+ *   ctvq_debug_set_fast_trace  8 %globaltimer stamps per CTA of vq_fwd_tc_fast_kernel into buf[SMs*8] (tools/trace_fast.py)
+ *   ctvq_debug_set_tc_dump     raw TMEM dot products of the generic tcgen05 kernel into buf (tools/debug_tc.py) */
+void ctvq_debug_set_fast_trace(unsigned long long* buf);
+void ctvq_debug_set_tc_dump(float* buf);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,8 @@ SHAPES = [
     (3, 256, 4, 8, 1, 256, 100, 1, "auto"),   # streaming kernel, d=256 (1 team)
     (1200, 64, 8, 8, 1, 64, 128, 1, "auto"),  # large enough for the single-codebook shared-atomic backward
     (5, 128, 8, 8, 1, 128, 64, 1, "auto"),    # config 3
+    (600, 128, 8, 8, 1, 128, 64, 1, "auto"),  # config 3, large enough for the C=1 TMA-ring backward (N >= 18944)
+    (7, 64, 16, 16, 1, 64, 300, 1, "auto"),   # resident-codebook forward, two units, partial last tile
     (3, 48, 8, 4, 2, 24, 50, 24, "auto"),     # generic tcgen05 kernel (K padded to 64, HW = 32)
     (2, 15, 3, 3, 5, 3, 7, 1, "auto"),        # ragged: SIMT + direct-atomic backward
     (6, 128, 8, 8, 4, 32, 64, 1, "simt"),

@@ -160,6 +160,14 @@ def test_pair_batching_matches_two_calls(env):
     ("cfg2_trained", 256, 128, 8, 8, 4, 64, "trained"),
     ("cfg2_big_tma_backward", 1024, 128, 8, 8, 4, 64, "trained"),  # large enough for the TMA-ring backward kernel
     ("cfg3_trained", 32, 128, 8, 8, 1, 64, "trained"),    # configs/ct_mcq_vae.yaml (x and y)
+    ("cfg3_big_tma_backward", 512, 128, 8, 8, 1, 64, "trained"),   # large enough for the C=1 TMA-ring backward kernel
+    ("cfg3_init_ties", 40, 128, 8, 8, 1, 64, "init"),
+    ("res_d64_k300", 24, 64, 16, 16, 1, 300, "trained"),  # resident-codebook kernel, ragged second unit
+    ("res_d32_k700", 12, 32, 16, 16, 1, 700, "init"),     # ... three units padded to four
+    ("res_d64_k64", 24, 64, 8, 8, 1, 64, "trained"),      # ... 64-column units
+    ("fast_c4_hw256", 8, 128, 16, 16, 4, 64, "trained"),  # neighbours of config 2 on the specialised tcgen05 forward
+    ("fast_c2_hw64", 40, 64, 8, 8, 2, 64, "init"),
+    ("fast_c2_hw256", 6, 64, 16, 16, 2, 50, "trained"),
     ("sweep_d32_k256", 256, 32, 16, 16, 1, 256, "trained"),
     ("sweep_d128_k1024", 64, 128, 16, 16, 1, 1024, "trained"),
     ("sweep_d256_k256", 16, 256, 16, 16, 1, 256, "init"),
