@@ -43,13 +43,13 @@ static int check_shape(int64_t B, int Dtot, int HW, int C, int d, int K, int cs,
     if (B <= 0 || Dtot <= 0 || HW <= 0 || C <= 0 || d <= 0 || K <= 0 || cs < 0) return CTVQ_E_BADARG;
     if (C > CTVQ_MAX_CODEBOOKS) return CTVQ_E_UNSUPPORTED;
     if ((int64_t)(C - 1) * cs + d > Dtot) return CTVQ_E_BADARG;
-    if (dtype != CTVQ_F32) return CTVQ_E_UNSUPPORTED;
+    if (dtype != CTVQ_F32 && dtype != CTVQ_BF16) return CTVQ_E_UNSUPPORTED;
     if (B * (int64_t)HW > (int64_t)1 << 40) return CTVQ_E_UNSUPPORTED;
     return CTVQ_OK;
 }
 
 static int fill(QuantParams& p, const void* const* codebooks, int64_t B, int Dtot, int HW, int C, int d, int K, int cs,
-                void* workspace, size_t ws_bytes) {
+                int dtype, void* workspace, size_t ws_bytes) {
     if (!codebooks || !workspace) return CTVQ_E_BADARG;
     if (ws_bytes < sizeof(Workspace)) return CTVQ_E_WORKSPACE;
     memset(&p, 0, sizeof(p));
@@ -70,11 +70,21 @@ static int fill(QuantParams& p, const void* const* codebooks, int64_t B, int Dto
     p.N = B * (int64_t)HW;
     p.n_seg = 1;
     p.Dtot = Dtot; p.HW = HW; p.C = C; p.d = d; p.K = K; p.cs = cs;
+    p.dtype = dtype;
     return CTVQ_OK;
 }
 
 static int dispatch_forward(const QuantParams& p, cudaStream_t s) {
     const int want = g_path.load();
+    if (p.dtype == CTVQ_BF16) {  // bf16 latents: the specialised kind::f16 kernel where it exists, else the SIMT kernel
+        if (want != CTVQ_PATH_SIMT) {
+            const int rc = launch_forward_tc_bf16(p, s);
+            if (rc != CTVQ_E_UNSUPPORTED) { t_last_path = CTVQ_PATH_TC; return rc; }
+            if (want == CTVQ_PATH_TC || want == CTVQ_PATH_TC_STREAM) return rc;
+        }
+        t_last_path = CTVQ_PATH_SIMT;
+        return launch_forward_simt(p, s);
+    }
     if (want == CTVQ_PATH_TC_STREAM) {
         t_last_path = CTVQ_PATH_TC;
         return launch_forward_tc_stream(p, s);
@@ -139,7 +149,7 @@ int ctvq_argmin(const void* const* z_segs, int n_seg, const void* const* codeboo
     int rc = check_shape(B, Dtot, HW, C, d, K, chan_stride, dtype);
     if (rc) return rc;
     QuantParams p;
-    rc = fill(p, codebooks, B, Dtot, HW, C, d, K, chan_stride, workspace, ws_bytes);
+    rc = fill(p, codebooks, B, Dtot, HW, C, d, K, chan_stride, dtype, workspace, ws_bytes);
     if (rc) return rc;
     p.n_seg = n_seg;
     for (int s = 0; s < n_seg; ++s) {
@@ -161,7 +171,7 @@ int ctvq_gather_st_loss(const void* z, const void* const* codebooks, const int64
     int rc = check_shape(B, Dtot, HW, C, d, K, chan_stride, dtype);
     if (rc) return rc;
     QuantParams p;
-    rc = fill(p, codebooks, B, Dtot, HW, C, d, K, chan_stride, workspace, ws_bytes);
+    rc = fill(p, codebooks, B, Dtot, HW, C, d, K, chan_stride, dtype, workspace, ws_bytes);
     if (rc) return rc;
     p.z[0] = static_cast<const float*>(z);
     p.idx[0] = reinterpret_cast<long long*>(const_cast<int64_t*>(idx));
@@ -181,7 +191,7 @@ int ctvq_forward(const void* z, const void* const* codebooks, int64_t B, int Dto
     int rc = check_shape(B, Dtot, HW, C, d, K, chan_stride, dtype);
     if (rc) return rc;
     QuantParams p;
-    rc = fill(p, codebooks, B, Dtot, HW, C, d, K, chan_stride, workspace, ws_bytes);
+    rc = fill(p, codebooks, B, Dtot, HW, C, d, K, chan_stride, dtype, workspace, ws_bytes);
     if (rc) return rc;
     p.z[0] = static_cast<const float*>(z);
     p.idx[0] = reinterpret_cast<long long*>(idx_out);
@@ -220,6 +230,7 @@ static int backward_impl(const void* z, const void* const* codebooks, const int6
     p.B = B; p.N = B * (int64_t)HW;
     p.Dtot = Dtot; p.HW = HW; p.C = C; p.d = d; p.K = K; p.cs = chan_stride;
     p.beta = beta;
+    p.dtype = dtype;
     if (peer_bufs) {  // arm the fused collective: the last CTA of whichever backward kernel runs all-reduces gE_out
         rc = make_peer_tail(p.peer, peer_bufs, world, rank, count_max, (size_t)C * K * d, epoch, scale, gE_reduced_out,
                             static_cast<Workspace*>(workspace));

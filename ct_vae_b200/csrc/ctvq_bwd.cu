@@ -17,8 +17,11 @@ namespace ctvq {
 namespace {
 constexpr int kBT = 256;  // threads
 
-template <int TM, int VEC>
+template <int TM, int VEC, typename T>
 __global__ void __launch_bounds__(kBT) vq_bwd_tile_kernel(const BwdParams p, const int use_es, const int ntiles) {
+    const T* __restrict__ zT = reinterpret_cast<const T*>(p.z);
+    const T* __restrict__ goT = reinterpret_cast<const T*>(p.g_out);
+    T* __restrict__ gzT = reinterpret_cast<T*>(p.gz);
     extern __shared__ __align__(16) float smem[];
     const int C = p.C, d = p.d, K = p.K, HW = p.HW, Dtot = p.Dtot, cs = p.cs;
     const int used = min(Dtot, (C - 1) * cs + d);
@@ -35,7 +38,7 @@ __global__ void __launch_bounds__(kBT) vq_bwd_tile_kernel(const BwdParams p, con
     if (use_es) {
         for (int i = tid; i < ckd; i += kBT) {
             const int j = i % d, ck = i / d;
-            es[ck * ESd + j] = __ldg(p.E[ck / K] + (size_t)(ck % K) * d + j);
+            es[ck * ESd + j] = IO<T>::cb(__ldg(p.E[ck / K] + (size_t)(ck % K) * d + j));
         }
     }
     const float gl = __ldg(p.g_loss);
@@ -64,9 +67,9 @@ __global__ void __launch_bounds__(kBT) vq_bwd_tile_kernel(const BwdParams p, con
                 }
                 idx_s[c * TM + m] = k;
             }
-            const float* src = p.z + (size_t)b * Dtot * HW + pp;
+            const T* src = zT + (size_t)b * Dtot * HW + pp;
             for (int ch = tid / TM; ch < used; ch += kBT / TM)
-                zs[ch * ZS + m] = valid ? __ldg(src + (size_t)ch * HW) : 0.0f;
+                zs[ch * ZS + m] = valid ? IO<T>::ld(src + (size_t)ch * HW) : 0.0f;
         }
         __syncthreads();
         // ---- phase 1: gz, lanes along HW ------------------------------------------------------------------
@@ -77,9 +80,9 @@ __global__ void __launch_bounds__(kBT) vq_bwd_tile_kernel(const BwdParams p, con
             const long long n = row0 + m;
             const long long b = n / HW;
             const int pp = (int)(n - b * HW);
-            float g[VEC];
+            float g[4];
 #pragma unroll
-            for (int u = 0; u < VEC; ++u) g[u] = 0.0f;
+            for (int u = 0; u < 4; ++u) g[u] = 0.0f;
             int c_hi, c_lo = 0;
             if (cs > 0) {
                 c_hi = min(ch / cs, C - 1);
@@ -89,27 +92,25 @@ __global__ void __launch_bounds__(kBT) vq_bwd_tile_kernel(const BwdParams p, con
             }
             for (int c = c_lo; c <= c_hi; ++c) {
                 const int j = ch - c * cs;
-                float go[VEC];
+                float go[4] = {0.f, 0.f, 0.f, 0.f};
                 const size_t goff = ((size_t)b * C * d + (size_t)c * d + j) * HW + pp;
                 if (VEC == 4) {
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.g_out) t = __ldg(reinterpret_cast<const float4*>(p.g_out + goff));
-                    go[0] = t.x; go[1 % VEC] = t.y; go[2 % VEC] = t.z; go[3 % VEC] = t.w;
+                    if (goT) IO<T>::ld4(goT + goff, go);
                 } else {
-                    go[0] = p.g_out ? __ldg(p.g_out + goff) : 0.0f;
+                    go[0] = goT ? IO<T>::ld(goT + goff) : 0.0f;
                 }
                 const float* __restrict__ Ec = p.E[c];
 #pragma unroll
                 for (int u = 0; u < VEC; ++u) {
                     const int k = idx_s[c * TM + m + u];
-                    const float e = use_es ? es[(c * K + k) * ESd + j] : __ldg(Ec + (size_t)k * d + j);
+                    const float e = use_es ? es[(c * K + k) * ESd + j] : IO<T>::cb(__ldg(Ec + (size_t)k * d + j));
                     const float diff = __fsub_rn(e, zs[ch * ZS + m + u]);  // q - z
                     g[u] += go[u] - coef_z * diff;
                 }
             }
-            float* dst = p.gz + ((size_t)b * Dtot + ch) * HW + pp;
-            if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]);
-            else *dst = g[0];
+            T* dst = gzT + ((size_t)b * Dtot + ch) * HW + pp;
+            if (VEC == 4) IO<T>::st4(dst, g);
+            else IO<T>::st(dst, g[0]);
         }
         // ---- phase 2: codebook-gradient accumulation, lanes along the channel -----------------------------------
         for (int item = warp; item < items; item += kBT / 32) {
@@ -128,10 +129,10 @@ __global__ void __launch_bounds__(kBT) vq_bwd_tile_kernel(const BwdParams p, con
                 const bool distinct = kk.x != kk.y && kk.x != kk.z && kk.x != kk.w && kk.y != kk.z && kk.y != kk.w &&
                                       kk.z != kk.w;
                 if (act) {
-                    const float e0 = use_es ? ec[kk.x * ESd] : __ldg(Ec + (size_t)kk.x * d + jj);
-                    const float e1 = use_es ? ec[kk.y * ESd] : __ldg(Ec + (size_t)kk.y * d + jj);
-                    const float e2 = use_es ? ec[kk.z * ESd] : __ldg(Ec + (size_t)kk.z * d + jj);
-                    const float e3 = use_es ? ec[kk.w * ESd] : __ldg(Ec + (size_t)kk.w * d + jj);
+                    const float e0 = use_es ? ec[kk.x * ESd] : IO<T>::cb(__ldg(Ec + (size_t)kk.x * d + jj));
+                    const float e1 = use_es ? ec[kk.y * ESd] : IO<T>::cb(__ldg(Ec + (size_t)kk.y * d + jj));
+                    const float e2 = use_es ? ec[kk.z * ESd] : IO<T>::cb(__ldg(Ec + (size_t)kk.z * d + jj));
+                    const float e3 = use_es ? ec[kk.w * ESd] : IO<T>::cb(__ldg(Ec + (size_t)kk.w * d + jj));
                     const float d0 = __fsub_rn(e0, zcol[m]), d1 = __fsub_rn(e1, zcol[m + 1]);
                     const float d2 = __fsub_rn(e2, zcol[m + 2]), d3 = __fsub_rn(e3, zcol[m + 3]);
                     if (distinct) {
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kBT) vq_bwd_tile_kernel(const BwdParams p, con
             for (; m < mcount; ++m) {
                 const int k = ks[m];
                 if (act) {
-                    const float e = use_es ? ec[k * ESd] : __ldg(Ec + (size_t)k * d + jj);
+                    const float e = use_es ? ec[k * ESd] : IO<T>::cb(__ldg(Ec + (size_t)k * d + jj));
                     ac[k * d] += __fsub_rn(e, zcol[m]);
                 }
             }
@@ -159,6 +160,11 @@ __global__ void __launch_bounds__(kBT) vq_bwd_tile_kernel(const BwdParams p, con
     peer_tail(p.peer, p.gE);  // fused collective (no-op unless ctvq_backward_allreduce armed it)
 }
 }  // namespace
+
+namespace {
+template <typename T>
+int launch_tiles(const BwdParams& p, int use_es, int ntiles, int grid, size_t sm, cudaStream_t s);
+}
 
 // returns CTVQ_E_UNSUPPORTED when the accumulator does not fit in shared memory (caller falls back)
 int launch_backward_tiled(const BwdParams& p, cudaStream_t s) {
@@ -184,19 +190,26 @@ int launch_backward_tiled(const BwdParams& p, cudaStream_t s) {
     // tiny batches against a big codebook: zeroing + flushing a [C,K,d] accumulator per CTA costs more than adding the
     // N*C*d differences straight into global memory -> let the caller fall back to the direct-atomic kernel
     if ((double)p.N * p.C * p.d < 2.0 * (double)grid * (double)ckd) return CTVQ_E_UNSUPPORTED;
-    const bool vec = (p.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.gz) & 15) == 0) &&
-                     (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 15) == 0);
+    return p.dtype == CTVQ_BF16 ? launch_tiles<__nv_bfloat16>(p, use_es, ntiles, grid, sm, s) : launch_tiles<float>(p, use_es, ntiles, grid, sm, s);
+}
+
+namespace {
+template <typename T>
+int launch_tiles(const BwdParams& p, int use_es, int ntiles, int grid, size_t sm, cudaStream_t s) {
+    constexpr int TM = 128;
+    const bool vec = (p.HW % 4 == 0) && IO<T>::aligned4(p.gz) && (p.g_out == nullptr || IO<T>::aligned4(p.g_out));
     cudaError_t e;
     if (vec) {
-        e = cudaFuncSetAttribute(vq_bwd_tile_kernel<TM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        e = cudaFuncSetAttribute(vq_bwd_tile_kernel<TM, 4, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return (int)e;
-        vq_bwd_tile_kernel<TM, 4><<<grid, kBT, sm, s>>>(p, use_es, ntiles);
+        vq_bwd_tile_kernel<TM, 4, T><<<grid, kBT, sm, s>>>(p, use_es, ntiles);
     } else {
-        e = cudaFuncSetAttribute(vq_bwd_tile_kernel<TM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        e = cudaFuncSetAttribute(vq_bwd_tile_kernel<TM, 1, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return (int)e;
-        vq_bwd_tile_kernel<TM, 1><<<grid, kBT, sm, s>>>(p, use_es, ntiles);
+        vq_bwd_tile_kernel<TM, 1, T><<<grid, kBT, sm, s>>>(p, use_es, ntiles);
     }
     return (int)cudaGetLastError();
 }
+}  // namespace
 
 }  // namespace ctvq

@@ -239,6 +239,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// four consecutive elements of a shared-memory row as floats (fp32: one LDS.128; bf16: one LDS.64, exact widening)
+__device__ __forceinline__ void lds4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void lds4(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+
 // One image (H*W = TM rows) per tile, one persistent CTA per SM, 12 warps:
 //   warps 0-3  "acc": register-prefetch the tile's indices + touched z channels one tile ahead, publish them in a
 //              double-buffered shared slot, accumulate the codebook gradient (warp-owned slabs, no atomics);
@@ -247,8 +258,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 //   warps 4-11 "gz": grad_z from shared memory only (128-bit LDS of g_out, codeword gathers), 128-bit stores.
 // No global load sits on any warp's critical path, so HBM stays busy with ~2 tiles of reads in flight per SM.
 constexpr int kBT4 = 384;
-template <int D, int C, int K, int HWT, int DTOT, int CS>
+// T: element type of z / g_out / grad_z (float, or __nv_bfloat16 for dtype = CTVQ_BF16: half the streamed bytes; codebook
+// values are rounded to bf16 as they are staged, all arithmetic stays fp32)
+template <int D, int C, int K, int HWT, int DTOT, int CS, typename T>
 __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, const int ntiles) {
+    const T* __restrict__ zT = reinterpret_cast<const T*>(p.z);
+    const T* __restrict__ goT = reinterpret_cast<const T*>(p.g_out);
+    T* __restrict__ gzT = reinterpret_cast<T*>(p.gz);
     constexpr int TM = HWT;                 // rows per tile = one image
     constexpr int NST = 3;                  // g_out ring depth
     constexpr int USED = (C - 1) * CS + D;
@@ -263,8 +279,8 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
     constexpr int kFull = 1, kEmpty = 3, kAcc = 5;
     static_assert(ITEMS <= 4 && TM == 64, "configs' shapes");
     extern __shared__ __align__(128) float smem[];
-    float* go_s = smem;                                   // [NST][C*D][TM]
-    int* idx_s = reinterpret_cast<int*>(go_s + NST * GOF);  // [2][C][TM]
+    T* go_s = reinterpret_cast<T*>(smem);                 // [NST][C*D][TM] in the I/O element type
+    int* idx_s = reinterpret_cast<int*>(smem + NST * GOF * sizeof(T) / sizeof(float));  // [2][C][TM]
     float* zs = reinterpret_cast<float*>(idx_s + 2 * C * TM);  // [2][USED][ZS]
     float* acc = zs + 2 * USED * ZS;                      // [2][C][K][D]  (one copy per row half)
     float* es = acc + 2 * CKD;                            // [C][K][D+1]
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
     for (int i = tid; i < 2 * CKD; i += kBT4) acc[i] = 0.0f;
     for (int i = tid; i < CKD; i += kBT4) {
         const int j = i % D, ck = i / D;
-        es[ck * ESD + j] = __ldg(p.E[ck / K] + (size_t)(ck % K) * D + j);
+        es[ck * ESD + j] = IO<T>::cb(__ldg(p.E[ck / K] + (size_t)(ck % K) * D + j));
     }
     const float gl = __ldg(p.g_loss);
     const double nd = (double)p.N * (double)D;
@@ -302,19 +318,19 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
                 const int c = half + 4 * i;
                 kreg[i] = (c < C) ? __ldg(p.idx + ((size_t)b * C + c) * HWT + m) : 0;
             }
-            const float* src = p.z + (size_t)b * DTOT * HWT + m;
+            const T* src = zT + (size_t)b * DTOT * HWT + m;
 #pragma unroll
             for (int i = 0; i < NZ; ++i) {
                 const int ch = half + 4 * i;
-                zreg[i] = (ch < USED) ? __ldg(src + (size_t)ch * HWT) : 0.0f;
+                zreg[i] = (ch < USED) ? IO<T>::ld(src + (size_t)ch * HWT) : 0.0f;
             }
         };
         auto issue_go = [&](int it) {  // thread 0: stream image it's g_out block into ring slot it % NST
             const int st = it % NST;
             if (it >= NST) mbar_wait(bar_empty + 8 * st, (uint32_t)((it / NST) - 1) & 1u);
             const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
-            mbar_expect_tx(bar_full + 8 * st, GOF * 4u);
-            bulk_g2s(smem_u32(go_s + st * GOF), p.g_out + (size_t)b * GOF, GOF * 4u, bar_full + 8 * st);
+            mbar_expect_tx(bar_full + 8 * st, GOF * (uint32_t)sizeof(T));
+            bulk_g2s(smem_u32(go_s + st * GOF), goT + (size_t)b * GOF, GOF * (uint32_t)sizeof(T), bar_full + 8 * st);
         };
         if (niter > 0) prefetch(0);
         if (tid == 0 && has_go)
@@ -391,11 +407,11 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
             const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
             const int* idb = idx_s + buf * C * TM;
             const float* zb = zs + buf * USED * ZS;
-            const float* gos = go_s + st * GOF;
-            float* gz_row = p.gz + (size_t)b * DTOT * HWT + m;
+            const T* gos = go_s + st * GOF;
+            T* gz_row = gzT + (size_t)b * DTOT * HWT + m;
             // zero channels first: they depend on nothing
-            for (int ch = USED + 2 * gw + hsel; ch < DTOT; ch += 2 * NGZ)
-                *reinterpret_cast<float4*>(gz_row + (size_t)ch * HWT) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int ch = USED + 2 * gw + hsel; ch < DTOT; ch += 2 * NGZ) IO<T>::st4(gz_row + (size_t)ch * HWT, zero4);
             named_sync(kFull + buf, kBT4);
             if (has_go) mbar_wait(bar_full + 8 * st, (uint32_t)(it / NST) & 1u);
             int eb[C][4];
@@ -407,20 +423,20 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
             }
             for (int ch = 2 * gw + hsel; ch < USED; ch += 2 * NGZ) {
                 const float z0 = zb[ch * ZS + m], z1 = zb[ch * ZS + m + 1], z2 = zb[ch * ZS + m + 2], z3 = zb[ch * ZS + m + 3];
-                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const int j = ch - c * CS;
                     if (j >= 0 && j < D) {
-                        float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (has_go) go = *reinterpret_cast<const float4*>(gos + (c * D + j) * TM + m);
+                        float go[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (has_go) lds4(gos + (c * D + j) * TM + m, go);
                         const float d0 = __fsub_rn(es[eb[c][0] + j], z0), d1 = __fsub_rn(es[eb[c][1] + j], z1);
                         const float d2 = __fsub_rn(es[eb[c][2] + j], z2), d3 = __fsub_rn(es[eb[c][3] + j], z3);
-                        g.x += go.x - coef_z * d0; g.y += go.y - coef_z * d1;
-                        g.z += go.z - coef_z * d2; g.w += go.w - coef_z * d3;
+                        g[0] += go[0] - coef_z * d0; g[1] += go[1] - coef_z * d1;
+                        g[2] += go[2] - coef_z * d2; g[3] += go[3] - coef_z * d3;
                     }
                 }
-                *reinterpret_cast<float4*>(gz_row + (size_t)ch * HWT) = g;
+                IO<T>::st4(gz_row + (size_t)ch * HWT, g);
             }
             __syncwarp();
             if (lane == 0 && has_go) mbar_arrive(bar_empty + 8 * st);  // ring slot may be refilled
@@ -435,10 +451,11 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
     peer_tail(p.peer, p.gE);  // fused collective: the last CTA pushes the finished gradient to every peer and reduces
 }
 
-template <int D, int C, int K, int HWT, int DTOT, int CS>
+template <int D, int C, int K, int HWT, int DTOT, int CS, typename T>
 int launch_tma(const BwdParams& p, cudaStream_t s) {
     constexpr int USED = (C - 1) * CS + D;
-    constexpr size_t smem = sizeof(float) * (3 * (size_t)C * D * HWT + 2 * (size_t)C * HWT + 2 * (size_t)USED * (HWT + 1) +
+    constexpr size_t smem = sizeof(T) * 3 * (size_t)C * D * HWT +
+                            sizeof(float) * (2 * (size_t)C * HWT + 2 * (size_t)USED * (HWT + 1) +
                                              2 * (size_t)C * K * D + (((size_t)C * K * (D + 1) + 1) & ~(size_t)1)) + 6 * 8;
     static_assert(smem <= 227 * 1024, "shared memory");
     if (p.N % HWT != 0) return CTVQ_E_UNSUPPORTED;
@@ -446,7 +463,7 @@ int launch_tma(const BwdParams& p, cudaStream_t s) {
     if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
     int grid = sm_count();
     if (grid > nt) grid = (int)nt;
-    auto kern = vq_bwd_tma_kernel<D, C, K, HWT, DTOT, CS>;
+    auto kern = vq_bwd_tma_kernel<D, C, K, HWT, DTOT, CS, T>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kBT4, smem, s>>>(p, (int)nt);
@@ -623,12 +640,20 @@ int launch_c1_tma(const BwdParams& p, cudaStream_t s) {
 int launch_backward_fast(const BwdParams& p, cudaStream_t s) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(p.gz) & 15) == 0) &&
                          (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 15) == 0);
-    if (!aligned) return CTVQ_E_UNSUPPORTED;
+    if (!aligned && p.dtype == CTVQ_F32) return CTVQ_E_UNSUPPORTED;
+    if (p.dtype == CTVQ_BF16) {
+        // configs/mcq_vae.yaml shape with bf16 I/O: the TMA-ring kernel streams half the bytes
+        const bool go16 = p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0;
+        if (p.d == 32 && p.C == 4 && p.K == 64 && p.HW == 64 && p.Dtot == 128 && p.cs == 1 && go16 && p.N % 64 == 0 &&
+            p.N >= (long long)sm_count() * 64 * 4 && (reinterpret_cast<uintptr_t>(p.gz) & 7) == 0)
+            return launch_tma<32, 4, 64, 64, 128, 1, __nv_bfloat16>(p, s);
+        return CTVQ_E_UNSUPPORTED;  // the tiled kernel (ctvq_bwd.cu) carries bf16 for every other shape
+    }
     static const bool no_tma = getenv("CTVQ_BWD_NO_TMA") != nullptr;  // A/B switch, read once per process
     // configs/mcq_vae.yaml: C=4, d=32, K=64, latents [B,128,8,8], overlapping slices
     if (p.d == 32 && p.C == 4 && p.K == 64 && p.HW == 64 && p.Dtot == 128 && p.cs == 1) {
         const bool go_ok = p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0;
-        if (go_ok && p.N >= (long long)sm_count() * 64 * 4 && !no_tma) return launch_tma<32, 4, 64, 64, 128, 1>(p, s);
+        if (go_ok && p.N >= (long long)sm_count() * 64 * 4 && !no_tma) return launch_tma<32, 4, 64, 64, 128, 1, float>(p, s);
         return launch<32, 4, 64, 64, 128, 1, 2>(p, s);
     }
     // configs/ct_mcq_vae.yaml: C=1, d=128, K=64, latents [B,128,8,8]

@@ -1,5 +1,6 @@
 // Shared declarations of the ctvq kernels (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,6 +29,45 @@ struct QuantParams {
     unsigned char* scratch;  // optional per-stream scratch behind the Workspace header (256-byte aligned), may be null
     size_t scratch_bytes;
     unsigned long long* neartie;  // optional device counter the kernels ADD near-tie rows to (include/ctvq.h), may be null
+    int dtype;  // CTVQ_F32 / CTVQ_BF16: element type behind z[] and q (codebooks are always the fp32 parameters)
+};
+
+// Element I/O of latents / outputs / gradients.  bf16 mode (include/ctvq.h) is the fp32 arithmetic contract applied to
+// bf16-ROUNDED operands: latents arrive as bf16 (exact in fp32), codebook values are rounded to bf16 as they are read
+// (cb), every product and sum is fp32, results are rounded to bf16 only when they are stored.
+template <typename T> struct IO;
+template <> struct IO<float> {
+    static constexpr int kDtype = CTVQ_F32;
+    static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+    static __device__ __forceinline__ void st4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+    static __device__ __forceinline__ float cb(float e) { return e; }
+    static __host__ __device__ __forceinline__ bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+};
+template <> struct IO<__nv_bfloat16> {
+    static constexpr int kDtype = CTVQ_BF16;
+    static __device__ __forceinline__ float ld(const __nv_bfloat16* p) {
+        return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+    }
+    static __device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+    static __device__ __forceinline__ void st4(__nv_bfloat16* p, const float (&v)[4]) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 t;
+        t.x = *reinterpret_cast<const unsigned*>(&a);
+        t.y = *reinterpret_cast<const unsigned*>(&b);
+        *reinterpret_cast<uint2*>(p) = t;
+    }
+    static __device__ __forceinline__ float cb(float e) { return __bfloat162float(__float2bfloat16_rn(e)); }
+    static __host__ __device__ __forceinline__ bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 };
 
 // Absolute term of the tensor-core candidate window, in units of (|z|^2 + max|e|^2): 2^-20 covers the fp32 rounding of
@@ -76,6 +116,7 @@ struct BwdParams {
     int Dtot, HW, C, d, K, cs;
     float beta;
     int smem_acc;  // 1: privatise the [C,K,d] accumulator in shared memory
+    int dtype;     // CTVQ_F32 / CTVQ_BF16: element type behind z, g_out, gz (idx int64, gE fp32, codebooks fp32)
     PeerTail peer; // world > 1: the last CTA all-reduces gE over NVLink peer memory (ctvq_backward_allreduce)
 };
 
@@ -107,6 +148,7 @@ int launch_latent_ce_bwd(const float* x, const long long* tgt, const float* rows
 int launch_forward_tc(const QuantParams& p, cudaStream_t s);  // returns CTVQ_E_UNSUPPORTED when shape not covered
 bool tc_supported(const QuantParams& p);
 int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s);  // shape-specialised tcgen05 kernels
+int launch_forward_tc_bf16(const QuantParams& p, cudaStream_t s);  // kind::f16 kernels for bf16 latents; CTVQ_E_UNSUPPORTED otherwise
 int launch_forward_tc_c1(const QuantParams& p, cudaStream_t s);    // single-codebook row-split tcgen05 kernels
 int launch_forward_tc_stream(const QuantParams& p, cudaStream_t s);  // single codebook of any size streamed through a TMA ring
 int launch_forward_tc_res(const QuantParams& p, cudaStream_t s);     // single codebook resident in shared memory (K <= 512 at D=64)

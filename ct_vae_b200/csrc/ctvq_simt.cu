@@ -72,7 +72,7 @@ constexpr int kTK = 64;       // codes per tile
 constexpr int kDJ = 32;       // channels per staged codebook chunk
 constexpr int kES = kDJ + 4;  // padded row stride of the codebook chunk (16B-group conflict-free LDS.128)
 
-template <int TM>
+template <int TM, typename T>
 __global__ void __launch_bounds__(256) vq_fwd_simt_kernel(const QuantParams p) {
     constexpr int RM = TM / 16;  // rows per thread
     extern __shared__ __align__(16) float smem[];
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) vq_fwd_simt_kernel(const QuantParams p) {
     const int c = blockIdx.y;
     const int seg = blockIdx.x / p.tiles_per_seg;
     const long long row0 = (long long)(blockIdx.x - seg * p.tiles_per_seg) * TM;
-    const float* __restrict__ z = p.z[seg];
+    const T* __restrict__ z = reinterpret_cast<const T*>(p.z[seg]);
     const float* __restrict__ E = p.E[c];
 
     // ---- stage the z tile: thread owns one row m, strides over channels (coalesced along HW) ----------
@@ -100,9 +100,9 @@ __global__ void __launch_bounds__(256) vq_fwd_simt_kernel(const QuantParams p) {
     const long long lb = lvalid ? ln / HW : 0;
     const int lp = lvalid ? (int)(ln - lb * HW) : 0;
     {
-        const float* src = z + ((size_t)lb * p.Dtot + (size_t)c * p.cs) * HW + lp;
+        const T* src = z + ((size_t)lb * p.Dtot + (size_t)c * p.cs) * HW + lp;
         for (int j = tid / TM; j < dpad; j += 256 / TM)
-            zs[(size_t)j * TM + lm] = (lvalid && j < d) ? __ldg(src + (size_t)j * HW) : 0.0f;
+            zs[(size_t)j * TM + lm] = (lvalid && j < d) ? IO<T>::ld(src + (size_t)j * HW) : 0.0f;
     }
     __syncthreads();
     if (tid < TM) {  // |z|^2, sequential FMA chain over ascending channel (arithmetic contract)
@@ -135,13 +135,14 @@ __global__ void __launch_bounds__(256) vq_fwd_simt_kernel(const QuantParams p) {
                     const int k = kt * kTK + kk, j = jc * kDJ + jq * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (k < K && j < d) v = __ldg(reinterpret_cast<const float4*>(E + (size_t)k * d + j));
+                    v = make_float4(IO<T>::cb(v.x), IO<T>::cb(v.y), IO<T>::cb(v.z), IO<T>::cb(v.w));
                     *reinterpret_cast<float4*>(es + kk * kES + jq * 4) = v;
                 }
             } else {
                 for (int e = tid; e < kTK * kDJ; e += 256) {
                     const int kk = e / kDJ, jj = e % kDJ;
                     const int k = kt * kTK + kk, j = jc * kDJ + jj;
-                    es[kk * kES + jj] = (k < K && j < d) ? __ldg(E + (size_t)k * d + j) : 0.0f;
+                    es[kk * kES + jj] = (k < K && j < d) ? IO<T>::cb(__ldg(E + (size_t)k * d + j)) : 0.0f;
                 }
             }
             __syncthreads();
@@ -222,26 +223,26 @@ __global__ void __launch_bounds__(256) vq_fwd_simt_kernel(const QuantParams p) {
     if (lvalid) {
         const int k = idx_s[lm];
         const float* e = E + (size_t)k * d;
-        float* out = p.q + ((size_t)lb * p.C * d + (size_t)c * d) * HW + lp;
+        T* out = reinterpret_cast<T*>(p.q) + ((size_t)lb * p.C * d + (size_t)c * d) * HW + lp;
         constexpr int PARTS = 256 / TM;
         const int part = tid / TM;
         if (e_vec) {
             for (int j = part * 4; j < d; j += PARTS * 4) {
                 const float4 q4 = __ldg(reinterpret_cast<const float4*>(e + j));
-                const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+                const float qv[4] = {IO<T>::cb(q4.x), IO<T>::cb(q4.y), IO<T>::cb(q4.z), IO<T>::cb(q4.w)};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float zv = zs[(size_t)(j + u) * TM + lm];
                     const float diff = __fsub_rn(qv[u], zv);
-                    out[(size_t)(j + u) * HW] = __fadd_rn(zv, diff);  // z + (q - z), models/vq_vae.py:53
+                    IO<T>::st(out + (size_t)(j + u) * HW, __fadd_rn(zv, diff));  // z + (q - z), models/vq_vae.py:53
                     lsum = fmaf(diff, diff, lsum);
                 }
             }
         } else {
             for (int j = part; j < d; j += PARTS) {
                 const float zv = zs[(size_t)j * TM + lm];
-                const float diff = __fsub_rn(__ldg(e + j), zv);
-                out[(size_t)j * HW] = __fadd_rn(zv, diff);
+                const float diff = __fsub_rn(IO<T>::cb(__ldg(e + j)), zv);
+                IO<T>::st(out + (size_t)j * HW, __fadd_rn(zv, diff));
                 lsum = fmaf(diff, diff, lsum);
             }
         }
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__(256) vq_fwd_simt_kernel(const QuantParams p) {
     if (last_block(p.ticket, gridDim.x * gridDim.y)) finalize_losses(p);
 }
 
-int launch_forward_simt(const QuantParams& p, cudaStream_t s) {
+template <typename T>
+static int launch_forward_simt_t(const QuantParams& p, cudaStream_t s) {
     const int dpad = (p.d + kDJ - 1) / kDJ * kDJ;
     auto smem_for = [&](int TM) { return (size_t)((size_t)dpad * TM + kTK * kES + TM + kTK + TM) * sizeof(float); };
     QuantParams q = p;
@@ -258,32 +260,37 @@ int launch_forward_simt(const QuantParams& p, cudaStream_t s) {
     if (smem_for(128) <= 200 * 1024) {
         q.tiles_per_seg = (int)((p.N + 127) / 128);
         const size_t sm = smem_for(128);
-        e = cudaFuncSetAttribute(vq_fwd_simt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        e = cudaFuncSetAttribute(vq_fwd_simt_kernel<128, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return (int)e;
         dim3 grid((unsigned)(q.tiles_per_seg * p.n_seg), (unsigned)p.C);
-        vq_fwd_simt_kernel<128><<<grid, 256, sm, s>>>(q);
+        vq_fwd_simt_kernel<128, T><<<grid, 256, sm, s>>>(q);
     } else if (smem_for(64) <= 200 * 1024) {
         q.tiles_per_seg = (int)((p.N + 63) / 64);
         const size_t sm = smem_for(64);
-        e = cudaFuncSetAttribute(vq_fwd_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        e = cudaFuncSetAttribute(vq_fwd_simt_kernel<64, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return (int)e;
         dim3 grid((unsigned)(q.tiles_per_seg * p.n_seg), (unsigned)p.C);
-        vq_fwd_simt_kernel<64><<<grid, 256, sm, s>>>(q);
+        vq_fwd_simt_kernel<64, T><<<grid, 256, sm, s>>>(q);
     } else {
         return CTVQ_E_UNSUPPORTED;
     }
     return (int)cudaGetLastError();
 }
 
+int launch_forward_simt(const QuantParams& p, cudaStream_t s) {
+    return p.dtype == CTVQ_BF16 ? launch_forward_simt_t<__nv_bfloat16>(p, s) : launch_forward_simt_t<float>(p, s);
+}
+
 // ------------------------------------------------------------------------------------------------
 // gather by supplied indices + straight-through + loss  (compute_latents)
 // ------------------------------------------------------------------------------------------------
-template <int VEC>
+template <int VEC, typename T>
 __global__ void __launch_bounds__(256) gather_st_loss_kernel(const QuantParams p) {
     __shared__ double red[32];
     const int c = blockIdx.y;
     const int d = p.d, HW = p.HW, HWV = HW / VEC;
-    const float* __restrict__ z = p.z[0];
+    const T* __restrict__ z = reinterpret_cast<const T*>(p.z[0]);
+    T* __restrict__ qout = reinterpret_cast<T*>(p.q);
     const float* __restrict__ E = p.E[c];
     const long long* __restrict__ idx = p.idx[0];
     const long long total = p.B * (long long)d * HWV;  // items of this codebook
@@ -297,53 +304,57 @@ __global__ void __launch_bounds__(256) gather_st_loss_kernel(const QuantParams p
         const size_t zoff = ((size_t)b * p.Dtot + (size_t)c * p.cs + j) * HW + (size_t)pv * VEC;
         const size_t ooff = ((size_t)b * p.C * d + (size_t)c * d + j) * HW + (size_t)pv * VEC;
         const size_t ioff = ((size_t)b * p.C + c) * HW + (size_t)pv * VEC;
-        float zv[VEC], ov[VEC];
+        float zv[4], ov[4];
         long long kv[VEC];
         if (VEC == 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(z + zoff));
-            zv[0] = t.x; zv[1 % VEC] = t.y; zv[2 % VEC] = t.z; zv[3 % VEC] = t.w;
+            IO<T>::ld4(z + zoff, zv);
             const longlong2 i0 = __ldg(reinterpret_cast<const longlong2*>(idx + ioff));
             const longlong2 i1 = __ldg(reinterpret_cast<const longlong2*>(idx + ioff + 2));
             kv[0] = i0.x; kv[1 % VEC] = i0.y; kv[2 % VEC] = i1.x; kv[3 % VEC] = i1.y;
         } else {
-            zv[0] = __ldg(z + zoff);
+            zv[0] = IO<T>::ld(z + zoff);
             kv[0] = __ldg(idx + ioff);
         }
 #pragma unroll
         for (int u = 0; u < VEC; ++u) {
             long long k = kv[u];
             if (k < 0 || k >= p.K) { atomicOr(p.err, 1u); k = k < 0 ? 0 : p.K - 1; }
-            const float diff = __fsub_rn(__ldg(E + (size_t)k * d + j), zv[u]);
+            const float diff = __fsub_rn(IO<T>::cb(__ldg(E + (size_t)k * d + j)), zv[u]);
             ov[u] = __fadd_rn(zv[u], diff);
             lsum = fmaf(diff, diff, lsum);
         }
-        if (VEC == 4)
-            *reinterpret_cast<float4*>(p.q + ooff) = make_float4(ov[0], ov[1 % VEC], ov[2 % VEC], ov[3 % VEC]);
-        else
-            p.q[ooff] = ov[0];
+        if (VEC == 4) IO<T>::st4(qout + ooff, ov);
+        else IO<T>::st(qout + ooff, ov[0]);
     }
     block_accumulate((double)lsum, &p.loss_acc[c], red);
     if (last_block(p.ticket, gridDim.x * gridDim.y)) finalize_losses(p);
 }
 
-int launch_gather(const QuantParams& p, cudaStream_t s) {
-    const bool vec = (p.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.z[0]) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(p.q) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.idx[0]) & 15) == 0);
+template <typename T>
+static int launch_gather_t(const QuantParams& p, cudaStream_t s) {
+    const bool vec = (p.HW % 4 == 0) && IO<T>::aligned4(p.z[0]) && IO<T>::aligned4(p.q) && ((reinterpret_cast<uintptr_t>(p.idx[0]) & 15) == 0);
     const long long items = p.B * (long long)p.d * (p.HW / (vec ? 4 : 1));
     long long blocks = (items + 256 * 4 - 1) / (256 * 4);
     if (blocks < 1) blocks = 1;
     if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     dim3 grid((unsigned)blocks, (unsigned)p.C);
-    if (vec) gather_st_loss_kernel<4><<<grid, 256, 0, s>>>(p);
-    else gather_st_loss_kernel<1><<<grid, 256, 0, s>>>(p);
+    if (vec) gather_st_loss_kernel<4, T><<<grid, 256, 0, s>>>(p);
+    else gather_st_loss_kernel<1, T><<<grid, 256, 0, s>>>(p);
     return (int)cudaGetLastError();
+}
+
+int launch_gather(const QuantParams& p, cudaStream_t s) {
+    return p.dtype == CTVQ_BF16 ? launch_gather_t<__nv_bfloat16>(p, s) : launch_gather_t<float>(p, s);
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int VEC>
+template <int VEC, typename T>
 __global__ void __launch_bounds__(256) backward_kernel(const BwdParams p) {
+    const T* __restrict__ zT = reinterpret_cast<const T*>(p.z);
+    const T* __restrict__ goT = reinterpret_cast<const T*>(p.g_out);
+    T* __restrict__ gzT = reinterpret_cast<T*>(p.gz);
     extern __shared__ float acc_s[];  // [C*K*d] when smem_acc
     const int d = p.d, HW = p.HW, HWV = HW / VEC, C = p.C, K = p.K;
     const int ckd = C * K * d;
@@ -363,9 +374,9 @@ __global__ void __launch_bounds__(256) backward_kernel(const BwdParams p) {
         const int ch = (int)(bch % p.Dtot);
         const long long b = bch / p.Dtot;
         const size_t zoff = ((size_t)b * p.Dtot + ch) * HW + (size_t)pv * VEC;
-        float g[VEC];
+        float g[4];
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) g[u] = 0.0f;
+        for (int u = 0; u < 4; ++u) g[u] = 0.0f;
         // codebooks whose slice [c*cs, c*cs+d) contains ch
         int c_hi = p.cs > 0 ? ch / p.cs : 0;
         if (c_hi > C - 1) c_hi = C - 1;
@@ -373,36 +384,30 @@ __global__ void __launch_bounds__(256) backward_kernel(const BwdParams p) {
         if (ch - d + 1 > 0) c_lo = p.cs > 0 ? (ch - d + 1 + p.cs - 1) / p.cs : 0;
         if (p.cs == 0) { c_lo = 0; c_hi = (ch < d) ? C - 1 : -1; }
         if (c_lo <= c_hi) {
-            float zv[VEC];
-            if (VEC == 4) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p.z + zoff));
-                zv[0] = t.x; zv[1 % VEC] = t.y; zv[2 % VEC] = t.z; zv[3 % VEC] = t.w;
-            } else {
-                zv[0] = __ldg(p.z + zoff);
-            }
+            float zv[4];
+            if (VEC == 4) IO<T>::ld4(zT + zoff, zv);
+            else zv[0] = IO<T>::ld(zT + zoff);
             for (int c = c_lo; c <= c_hi; ++c) {
                 const int j = ch - c * p.cs;
                 const size_t ioff = ((size_t)b * C + c) * HW + (size_t)pv * VEC;
                 const size_t goff = ((size_t)b * C * d + (size_t)c * d + j) * HW + (size_t)pv * VEC;
                 long long kv[VEC];
-                float go[VEC];
+                float go[4] = {0.f, 0.f, 0.f, 0.f};
                 if (VEC == 4) {
                     const longlong2 i0 = __ldg(reinterpret_cast<const longlong2*>(p.idx + ioff));
                     const longlong2 i1 = __ldg(reinterpret_cast<const longlong2*>(p.idx + ioff + 2));
                     kv[0] = i0.x; kv[1 % VEC] = i0.y; kv[2 % VEC] = i1.x; kv[3 % VEC] = i1.y;
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.g_out) t = __ldg(reinterpret_cast<const float4*>(p.g_out + goff));
-                    go[0] = t.x; go[1 % VEC] = t.y; go[2 % VEC] = t.z; go[3 % VEC] = t.w;
+                    if (goT) IO<T>::ld4(goT + goff, go);
                 } else {
                     kv[0] = __ldg(p.idx + ioff);
-                    go[0] = p.g_out ? __ldg(p.g_out + goff) : 0.0f;
+                    go[0] = goT ? IO<T>::ld(goT + goff) : 0.0f;
                 }
                 const float* __restrict__ E = p.E[c];
 #pragma unroll
                 for (int u = 0; u < VEC; ++u) {
                     long long k = kv[u];
                     if (k < 0 || k >= K) { atomicOr(p.err, 1u); k = k < 0 ? 0 : K - 1; }
-                    const float diff = __fsub_rn(__ldg(E + (size_t)k * d + j), zv[u]);  // q - z
+                    const float diff = __fsub_rn(IO<T>::cb(__ldg(E + (size_t)k * d + j)), zv[u]);  // q - z
                     g[u] += go[u] - coef_z * diff;
                     const int a = (c * K + (int)k) * d + j;
                     if (p.smem_acc) atomicAdd(&acc_s[a], diff);
@@ -410,8 +415,8 @@ __global__ void __launch_bounds__(256) backward_kernel(const BwdParams p) {
                 }
             }
         }
-        if (VEC == 4) *reinterpret_cast<float4*>(p.gz + zoff) = make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]);
-        else p.gz[zoff] = g[0];
+        if (VEC == 4) IO<T>::st4(gzT + zoff, g);
+        else IO<T>::st(gzT + zoff, g[0]);
     }
     if (p.smem_acc) {
         __syncthreads();
@@ -423,21 +428,10 @@ __global__ void __launch_bounds__(256) backward_kernel(const BwdParams p) {
     peer_tail(p.peer, p.gE);  // fused collective (no-op unless ctvq_backward_allreduce armed it)
 }
 
-int launch_backward(const BwdParams& p0, cudaStream_t s) {
-    BwdParams p = p0;
-    cudaError_t e = cudaMemsetAsync(p.gE, 0, sizeof(float) * (size_t)p.C * p.K * p.d, s);
-    if (e != cudaSuccess) return (int)e;
-    {
-        int rc = launch_backward_c1(p, s);    // one full-width codebook at a batch that amortises a per-CTA accumulator
-        if (rc != CTVQ_E_UNSUPPORTED) return rc;
-        rc = launch_backward_fast(p, s);      // shape-specialised (configs' shapes)
-        if (rc != CTVQ_E_UNSUPPORTED) return rc;
-        rc = launch_backward_tiled(p, s);     // shared-memory accumulator, no atomics in the inner loop
-        if (rc != CTVQ_E_UNSUPPORTED) return rc;
-    }
-    const bool vec = (p.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.z) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(p.gz) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.idx) & 15) == 0) &&
-                     (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 15) == 0);
+template <typename T>
+static int launch_backward_direct(BwdParams p, cudaStream_t s) {
+    const bool vec = (p.HW % 4 == 0) && IO<T>::aligned4(p.z) && IO<T>::aligned4(p.gz) && ((reinterpret_cast<uintptr_t>(p.idx) & 15) == 0) &&
+                     (p.g_out == nullptr || IO<T>::aligned4(p.g_out));
     const long long items = p.B * (long long)p.Dtot * (p.HW / (vec ? 4 : 1));
     const size_t acc_bytes = sizeof(float) * (size_t)p.C * p.K * p.d;
     p.smem_acc = (acc_bytes <= 64 * 1024 && p.N >= 32768) ? 1 : 0;
@@ -446,20 +440,37 @@ int launch_backward(const BwdParams& p0, cudaStream_t s) {
     const long long cap = p.smem_acc ? sm_count() * 2 : sm_count() * 16;
     if (blocks > cap) blocks = cap;
     const size_t sm = p.smem_acc ? acc_bytes : 0;
+    cudaError_t e;
     if (vec) {
         if (sm > 48 * 1024) {
-            e = cudaFuncSetAttribute(backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            e = cudaFuncSetAttribute(backward_kernel<4, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             if (e != cudaSuccess) return (int)e;
         }
-        backward_kernel<4><<<(unsigned)blocks, 256, sm, s>>>(p);
+        backward_kernel<4, T><<<(unsigned)blocks, 256, sm, s>>>(p);
     } else {
         if (sm > 48 * 1024) {
-            e = cudaFuncSetAttribute(backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            e = cudaFuncSetAttribute(backward_kernel<1, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             if (e != cudaSuccess) return (int)e;
         }
-        backward_kernel<1><<<(unsigned)blocks, 256, sm, s>>>(p);
+        backward_kernel<1, T><<<(unsigned)blocks, 256, sm, s>>>(p);
     }
     return (int)cudaGetLastError();
+}
+
+int launch_backward(const BwdParams& p0, cudaStream_t s) {
+    BwdParams p = p0;
+    cudaError_t e = cudaMemsetAsync(p.gE, 0, sizeof(float) * (size_t)p.C * p.K * p.d, s);
+    if (e != cudaSuccess) return (int)e;
+    {
+        int rc = CTVQ_E_UNSUPPORTED;
+        if (p.dtype == CTVQ_F32) rc = launch_backward_c1(p, s);  // one full-width codebook at a batch that amortises a per-CTA accumulator
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
+        rc = launch_backward_fast(p, s);      // shape-specialised (configs' shapes), fp32 and bf16
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
+        rc = launch_backward_tiled(p, s);     // shared-memory accumulator, no atomics in the inner loop
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
+    }
+    return p.dtype == CTVQ_BF16 ? launch_backward_direct<__nv_bfloat16>(p, s) : launch_backward_direct<float>(p, s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -27,12 +27,12 @@ def _shape(latents: Tensor, codebooks: Sequence[Tensor], chan_stride: int):
     return b, dtot, h, w, c, d, k
 
 
-def _bf16_operands(z: Tensor, es: Sequence[Tensor]):
-    """bf16 mode (not defined by the reference — `.bfloat16()` raises at models/vq_vae.py:43): the fp32 contract
-    applied to bf16-ROUNDED latents and codebooks.  bf16 values are exact in fp32, so the kernels run
-    unchanged on up-cast copies; outputs are rounded to bf16 by the caller.  (Native bf16 tiles, which would halve
-    the HBM bytes, are next-round work: today this mode costs extra cast passes.)"""
-    return z.float(), [e.to(torch.bfloat16).float() for e in es]
+def _dtype_code(t: Tensor) -> int:
+    """bf16 mode (not defined by the reference -- `.bfloat16()` raises at models/vq_vae.py:43): the fp32 arithmetic contract
+    applied to bf16-ROUNDED latents and codebooks, NATIVE in the kernels: latents, outputs and their
+    gradients cross HBM as bf16 (half the bytes), the fp32 codebook parameters are rounded to bf16 as they are read,
+    every product and sum is fp32, indices stay int64, losses and codebook gradients stay fp32."""
+    return _lib.BF16 if t.dtype == torch.bfloat16 else _lib.F32
 
 
 def _counter_ptr(counter: Optional[Tensor], dev) -> Optional[int]:
@@ -59,15 +59,9 @@ def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], ch
     zs = [z.detach().contiguous() for z in latents_list]
     es = [e.detach() for e in codebooks]
     b, dtot, h, w, c, d, k = _shape(zs[0], es, chan_stride)
-    if zs[0].dtype == torch.bfloat16:
-        zs32 = []
-        for z in zs:
-            z32, es = _bf16_operands(z, [e.detach() for e in codebooks])
-            zs32.append(z32)
-        zs = zs32
     for z in zs[1:]:
-        if z.shape != zs[0].shape:
-            raise RuntimeError("paired inputs must share a shape")
+        if z.shape != zs[0].shape or z.dtype != zs[0].dtype:
+            raise RuntimeError("paired inputs must share a shape and dtype")
     dev = zs[0].device
     outs = [torch.empty((b, c, h, w), dtype=torch.int64, device=dev) for _ in zs]
     if b == 0 or h * w == 0:
@@ -75,7 +69,7 @@ def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], ch
     sp = _lib.stream_ptr(dev)
     ws = _lib.workspace(dev, sp, c, k, d)
     rc = _lib.lib().ctvq_argmin(_lib.ptr_array(zs), len(zs), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride,
-                                _lib.F32, _lib.ptr_array(outs), _counter_ptr(counter, dev), ws.data_ptr(), ws.numel(),
+                                _dtype_code(zs[0]), _lib.ptr_array(outs), _counter_ptr(counter, dev), ws.data_ptr(), ws.numel(),
                                 dev.index, sp)
     _lib.check(rc, "ctvq_argmin")
     return outs
@@ -107,8 +101,7 @@ class _Quantize(torch.autograd.Function):
             ctx.set_materialize_grads(False)
             return torch.empty((b, c * d, h, w), dtype=io_dtype, device=dev), nan, empty_inds, per
         ctx.empty = False
-        if io_dtype == torch.bfloat16:
-            z, es = _bf16_operands(z, es)
+        dt = _dtype_code(z)
         out = torch.empty((b, c * d, h, w), dtype=z.dtype, device=dev)
         losses = torch.empty(c + 1, dtype=torch.float32, device=dev)
         sp = _lib.stream_ptr(dev)
@@ -116,7 +109,7 @@ class _Quantize(torch.autograd.Function):
         L = _lib.lib()
         if given_inds is None:
             inds = torch.empty((b, c, h, w), dtype=torch.int64, device=dev)
-            rc = L.ctvq_forward(z.data_ptr(), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride, _lib.F32,
+            rc = L.ctvq_forward(z.data_ptr(), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride, dt,
                                 float(beta), inds.data_ptr(), out.data_ptr(), losses.data_ptr(),
                                 _counter_ptr(counter, dev), ws.data_ptr(), ws.numel(), dev.index, sp)
             _lib.check(rc, "ctvq_forward")
@@ -126,15 +119,13 @@ class _Quantize(torch.autograd.Function):
                 raise RuntimeError(f"indices have {given_inds.numel()} elements, expected {b * c * h * w}")
             inds = given_inds.detach().to(torch.int64).reshape(b, c, h, w).contiguous()
             rc = L.ctvq_gather_st_loss(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), b, dtot, h * w, c, d, k,
-                                       chan_stride, _lib.F32, float(beta), out.data_ptr(), losses.data_ptr(),
+                                       chan_stride, dt, float(beta), out.data_ptr(), losses.data_ptr(),
                                        ws.data_ptr(), ws.numel(), dev.index, sp)
             _lib.check(rc, "ctvq_gather_st_loss")
             _lib.maybe_validate(ws, dev, sp, "compute_latents")
         ctx.save_for_backward(z, inds, *es)
         ctx.meta = (float(beta), int(chan_stride), b, dtot, h, w, c, d, k, comm)
         ctx.io_dtype = io_dtype
-        if io_dtype == torch.bfloat16:
-            out = out.to(torch.bfloat16)
         per = losses[:c]
         ctx.mark_non_differentiable(inds, per)
         ctx.set_materialize_grads(False)  # unused outputs arrive as None: no zero-fill kernels, no host sync
@@ -157,8 +148,9 @@ class _Quantize(torch.autograd.Function):
             g_loss = torch.zeros((), dtype=torch.float32, device=dev)
         g_loss = g_loss.to(torch.float32).contiguous()
         go_ptr = None
+        dt = _dtype_code(z)
         if g_out is not None:
-            g_out = g_out.contiguous().float()
+            g_out = g_out.contiguous().to(z.dtype)
             go_ptr = g_out.data_ptr()
         gz = torch.empty_like(z)
         ge = torch.empty((c, k, d), dtype=torch.float32, device=dev)
@@ -169,7 +161,7 @@ class _Quantize(torch.autograd.Function):
             table, world, rank, cmax, epoch, scale = comm.peer_args(c * k * d)
             red = torch.empty((c, k, d), dtype=torch.float32, device=dev)
             rc = _lib.lib().ctvq_backward_allreduce(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), go_ptr,
-                                                    g_loss.data_ptr(), b, dtot, h * w, c, d, k, cs, _lib.F32, beta,
+                                                    g_loss.data_ptr(), b, dtot, h * w, c, d, k, cs, dt, beta,
                                                     gz.data_ptr(), ge.data_ptr(), table, world, rank, cmax, epoch, scale,
                                                     red.data_ptr(), ws.data_ptr(), ws.numel(), dev.index, sp)
             _lib.check(rc, "ctvq_backward_allreduce")
@@ -177,14 +169,12 @@ class _Quantize(torch.autograd.Function):
             comm = None
         else:
             rc = _lib.lib().ctvq_backward(z.data_ptr(), _lib.ptr_array(es), inds.data_ptr(), go_ptr, g_loss.data_ptr(),
-                                          b, dtot, h * w, c, d, k, cs, _lib.F32, beta, gz.data_ptr(), ge.data_ptr(),
+                                          b, dtot, h * w, c, d, k, cs, dt, beta, gz.data_ptr(), ge.data_ptr(),
                                           ws.data_ptr(), ws.numel(), dev.index, sp)
             _lib.check(rc, "ctvq_backward")
         _lib.maybe_validate(ws, dev, sp, "quantiser backward")
         if comm is not None:
             ge = comm.allreduce_(ge)  # the one collective of the path (NCCL), on the backward kernel's stream
-        if ctx.io_dtype == torch.bfloat16:
-            gz = gz.to(torch.bfloat16)
         return (gz, None, None, None, None, None, *ge.unbind(0))
 
 

@@ -1,6 +1,6 @@
-"""Benchmark harness pieces that sit AROUND the hot path (not part of it): a stand-in for the MCQ-VAE model
-shell and for the Lightning training step, needed because neither the reference tree nor pytorch_lightning
-exists on the GPU box.
+"""Harness pieces that sit AROUND the hot path (not part of it): a stand-in for the MCQ-VAE model shell and for the
+Lightning training step (bench only: neither the reference tree nor pytorch_lightning exists on the GPU box), and the
+logging hygiene of SURVEY.md §8(f) rank 3 (``fused_log_all`` / ``install_experiment``).
 
 * ``MCQVAEShell`` has the layer structure of models/mcq_vae.py:142-317 (stride-2 4x4 conv encoder, 3x3 conv,
   six residual layers, 1x1 conv to the embedding dimension; mirrored decoder with transposed convs and tanh)
@@ -148,3 +148,58 @@ class GraphedTrainer:
         else:
             self.opt.step()
         return self.loss
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# harness hygiene: experiment.py:87-110
+# ----------------------------------------------------------------------------------------------------------------------
+def _is_scalar(val) -> bool:
+    # the reference's own test (experiment.py:95): a 0-d tensor or a 1-element 1-d tensor
+    return type(val) == torch.Tensor and (len(val.shape) == 0 or (len(val.shape) == 1 and val.size(0) == 1))
+
+
+def fused_log_all(self, losses: dict, batch_size, validation: bool = False, _orig=None):
+    """Drop-in for ``VAEXperiment.log_all`` (experiment.py:87-110) with the same logged keys and values, but
+
+      * ONE device->host transfer per step for all scalar entries (the reference calls ``.item()`` per scalar,
+        experiment.py:96: three to ten stream synchronisations per step), and
+      * ONE all-reduce of the stacked scalars per step when training is distributed (the reference asks Lightning for
+        ``sync_dist=True`` per key, experiment.py:110: one small NCCL all-reduce per logged scalar per step), after which
+        ``log_dict`` is called with ``sync_dist=False`` on plain floats -- the same mean-over-ranks values.
+
+    Non-scalar entries (images) keep the reference's handling: they are passed to the original method."""
+    if validation:
+        losses = {f"val_{key}": val for key, val in losses.items()}
+    scalars = {k: v for k, v in losses.items() if _is_scalar(v)}
+    others = {k: v for k, v in losses.items() if not _is_scalar(v)}
+    values = {}
+    if scalars:
+        devs = {v.device for v in scalars.values()}
+        dev = next((d for d in devs if d.type == "cuda"), next(iter(devs)))
+        flat = torch.stack([v.detach().reshape(()).to(device=dev, dtype=torch.float32, non_blocking=True)
+                            for v in scalars.values()])
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(flat)                      # one collective for every logged scalar of the step
+            flat = flat / dist.get_world_size()        # sync_dist=True reduces with the mean
+        values = dict(zip(scalars.keys(), flat.tolist()))  # one synchronisation
+    if others and _orig is not None:
+        _orig(self, dict(others), batch_size, validation=False)  # keys already carry their val_ prefix
+    if values:
+        self.log_dict(values, sync_dist=False, batch_size=batch_size)
+    return values
+
+
+def install_experiment(experiment_cls) -> bool:
+    """Rebind ``log_all`` of the reference's ``VAEXperiment`` class (experiment.py:17) to the fused version.  Idempotent."""
+    orig = experiment_cls.__dict__.get("log_all")
+    if orig is None or getattr(orig, "_ctvq_fused", False):
+        return False
+
+    def log_all(self, losses: dict, batch_size, validation: bool = False):
+        return fused_log_all(self, losses, batch_size, validation, _orig=orig)
+
+    log_all._ctvq_fused = True
+    log_all.__wrapped__ = orig
+    experiment_cls.log_all = log_all
+    return True

@@ -110,7 +110,61 @@ def test_error_convention_on_device():
     args = lambda dt, d, wsn: (z.data_ptr(), ptrs, 2, 8, 4, 1, d, 4, 1, dt, 0.25, idx.data_ptr(), out.data_ptr(),
                                loss.data_ptr(), None, ws.data_ptr(), wsn, 0, sp)
     assert L.ctvq_forward(*args(0, 8, ws.numel())) == 0
-    assert L.ctvq_forward(*args(1, 8, ws.numel())) == -2       # CTVQ_BF16 pointers: unsupported in this build
+    assert L.ctvq_forward(*args(7, 8, ws.numel())) == -2       # unknown dtype code (CTVQ_F32 = 0 and CTVQ_BF16 = 1 exist)
     assert L.ctvq_forward(*args(0, 9, ws.numel())) == -1       # slice exceeds the channel count
     assert L.ctvq_forward(*args(0, 8, 8)) == -3                # workspace too small
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("shape", [
+    (6, 128, 8, 8, 4, 32, 64, 1),      # config 2 (bf16 kind::f16 forward / bf16 backward where specialised)
+    (300, 128, 8, 8, 4, 32, 64, 1),    # ... large enough for the persistent kernels
+    (3, 64, 16, 16, 1, 64, 300, 1),    # generic bf16 path (SIMT forward, tiled backward)
+    (2, 15, 3, 3, 5, 3, 7, 1),         # ragged: scalar loads / stores
+])
+def test_bf16_through_the_c_abi(shape):
+    """dtype = CTVQ_BF16: latents / output / g_out / grad_z are bf16 device buffers, codebooks stay the fp32 parameters
+    (rounded to bf16 inside the kernels).  Guard bands, exact indices vs the C oracle on the rounded operands, bit-exact
+    bf16 output, gradients at north_star's bf16 tolerance (2e-2; grad_E is fp32: 1e-5)."""
+    from ct_vae_b200 import _lib
+    from oracle import c_oracle as CO
+    B, Dtot, H, W, C, d, K, cs = shape
+    HW = H * W
+    dev = torch.device("cuda:0")
+    L = _lib.lib()
+    torch.manual_seed(4)
+    z = torch.randn(B, Dtot, H, W, device=dev).to(torch.bfloat16)
+    books = [torch.randn(K, d, device=dev) * 0.5 for _ in range(C)]
+    ptrs = (ctypes.c_void_p * C)(*[e.data_ptr() for e in books])
+    ws = torch.zeros(L.ctvq_workspace_bytes(C, K, d), dtype=torch.uint8, device=dev)
+    sp = torch.cuda.current_stream(dev).cuda_stream
+    n_out, n_idx = B * C * d * HW, B * C * HW
+    S16 = -3.0
+    out_b, out = _guarded(n_out, torch.bfloat16, dev, S16)
+    idx_b, idx = _guarded(n_idx, torch.int64, dev, SENT_I)
+    loss_b, loss = _guarded(C + 1, torch.float32, dev, SENT_F)
+    rc = L.ctvq_forward(z.data_ptr(), ptrs, B, Dtot, HW, C, d, K, cs, 1, 0.25, idx.data_ptr(), out.data_ptr(),
+                        loss.data_ptr(), None, ws.data_ptr(), ws.numel(), 0, sp)
+    assert rc == 0, L.ctvq_strerror(rc)
+    torch.cuda.synchronize()
+    assert _intact(out_b, n_out, S16) and _intact(idx_b, n_idx, SENT_I) and _intact(loss_b, C + 1, SENT_F)
+    zr = z.float().cpu()
+    er = [e.to(torch.bfloat16).float().cpu() for e in books]
+    ref_idx = CO.argmin(zr, er, cs)
+    assert torch.equal(idx.cpu().view(B, C, H, W), ref_idx)
+    ref_q, ref_loss = CO.gather_st_loss(zr, ref_idx, er, 0.25, cs)
+    assert torch.equal(out.float().cpu().view_as(ref_q), ref_q.to(torch.bfloat16).float())
+    assert abs(float(loss[C]) - float(ref_loss[C])) <= 1e-5 * abs(float(ref_loss[C]))
+    g_out = torch.randn(B, C * d, H, W, device=dev).to(torch.bfloat16)
+    g_loss = torch.full((1,), 0.7, device=dev)
+    n_gz, n_ge = B * Dtot * HW, C * K * d
+    gz_b, gz = _guarded(n_gz, torch.bfloat16, dev, S16)
+    ge_b, ge = _guarded(n_ge, torch.float32, dev, SENT_F)
+    rc = L.ctvq_backward(z.data_ptr(), ptrs, idx.data_ptr(), g_out.data_ptr(), g_loss.data_ptr(), B, Dtot, HW, C, d, K, cs,
+                         1, 0.25, gz.data_ptr(), ge.data_ptr(), ws.data_ptr(), ws.numel(), 0, sp)
+    assert rc == 0, L.ctvq_strerror(rc)
+    torch.cuda.synchronize()
+    assert _intact(gz_b, n_gz, S16) and _intact(ge_b, n_ge, SENT_F)
+    ref_gz, ref_ge = CO.backward(zr, ref_idx, er, 0.25, g_out.float().cpu(), 0.7, cs)
+    assert float((gz.float().cpu().view_as(ref_gz) - ref_gz).abs().max() / ref_gz.abs().max()) < 2e-2
+    assert float((ge.cpu().view_as(ref_ge) - ref_ge).abs().max() / ref_ge.abs().max().clamp_min(1e-30)) < 1e-5
