@@ -56,19 +56,13 @@ __device__ __forceinline__ void peer_push_reduce(const PeerTail& t, const float*
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t slot = ((size_t)(t.epoch & 1u) * t.world + t.rank) * t.count_max;
     const size_t n4 = t.count >> 2;
-    // (1) push: four 128-bit loads in flight per thread (the message is a few float4 per thread: latency, not bandwidth)
-    for (size_t i0 = tid; i0 < n4; i0 += 4 * (size_t)nt) {
-        float4 v[4];
+    // (1) push (register-light on purpose: this tail is inlined into every backward kernel and must not raise their
+    // register count -- an unrolled version cost the single-codebook kernels their second CTA per SM; the loads are L2 hits)
+    for (size_t i = tid; i < n4; i += nt) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src) + i);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (i0 + (size_t)u * nt < n4) v[u] = __ldcg(reinterpret_cast<const float4*>(src) + i0 + (size_t)u * nt);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (i0 + (size_t)u * nt < n4) {
-#pragma unroll
-                for (int r = 0; r < CTVQ_MAX_PEERS; ++r)
-                    if (r < t.world) reinterpret_cast<float4*>(t.recv[r] + slot)[i0 + (size_t)u * nt] = v[u];
-            }
+        for (int r = 0; r < CTVQ_MAX_PEERS; ++r)
+            if (r < t.world) reinterpret_cast<float4*>(t.recv[r] + slot)[i] = v;
     }
     for (size_t i = (n4 << 2) + tid; i < t.count; i += nt) {
         const float v = __ldcg(src + i);
@@ -90,23 +84,15 @@ __device__ __forceinline__ void peer_push_reduce(const PeerTail& t, const float*
     __syncthreads();
     // (4) rank-ordered sum of the local slots
     const float* base = t.recv[t.rank] + (size_t)(t.epoch & 1u) * t.world * t.count_max;
-    for (size_t i0 = tid; i0 < n4; i0 += 2 * (size_t)nt) {  // two float4 x `world` slots = up to 16 loads in flight per thread
-        float4 v[2][CTVQ_MAX_PEERS];
+    for (size_t i = tid; i < n4; i += nt) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int r = 0; r < CTVQ_MAX_PEERS; ++r)
-                if (r < t.world && i0 + (size_t)u * nt < n4)
-                    v[u][r] = __ldcv(reinterpret_cast<const float4*>(base + (size_t)r * t.count_max) + i0 + (size_t)u * nt);
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-            if (i0 + (size_t)u * nt < n4) {
-                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int r = 0; r < CTVQ_MAX_PEERS; ++r)  // rank order: the same association on every rank
-                    if (r < t.world) { s.x += v[u][r].x; s.y += v[u][r].y; s.z += v[u][r].z; s.w += v[u][r].w; }
-                reinterpret_cast<float4*>(t.out)[i0 + (size_t)u * nt] = make_float4(s.x * t.scale, s.y * t.scale, s.z * t.scale, s.w * t.scale);
+        for (int r = 0; r < CTVQ_MAX_PEERS; ++r)  // rank order: the same association on every rank
+            if (r < t.world) {
+                const float4 v = __ldcv(reinterpret_cast<const float4*>(base + (size_t)r * t.count_max) + i);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             }
+        reinterpret_cast<float4*>(t.out)[i] = make_float4(s.x * t.scale, s.y * t.scale, s.z * t.scale, s.w * t.scale);
     }
     for (size_t i = (n4 << 2) + tid; i < t.count; i += nt) {
         float s = 0.0f;

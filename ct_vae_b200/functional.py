@@ -35,6 +35,16 @@ def _dtype_code(t: Tensor) -> int:
     return _lib.BF16 if t.dtype == torch.bfloat16 else _lib.F32
 
 
+def _bf16_via_fp32(b, dtot, hw, c, d, k, cs) -> bool:
+    """bf16 latents run NATIVELY (dtype = CTVQ_BF16: bf16 TMA slabs, tcgen05.mma.kind::f16, bf16 streams in the backward)
+    on the multi-codebook shape of configs/mcq_vae.yaml, and natively on the generic kernels for small problems.  Large
+    problems of any OTHER shape have no 16-bit tensor-core kernel yet: they are up-cast once and take the fp32 tcgen05
+    kernels (bf16 values are exact in fp32 and the codebook is rounded first, so the result is the same contract), which is
+    10x faster there than the generic bf16 kernels despite the two cast passes."""
+    native_shape = d == 32 and cs == 1 and k <= 64 and c == 4 and hw == 64 and dtot == 128
+    return (not native_shape) and b * hw * c * k * d > (1 << 24)
+
+
 def _counter_ptr(counter: Optional[Tensor], dev) -> Optional[int]:
     if counter is None:
         return None
@@ -66,6 +76,9 @@ def compute_inds(latents_list: Sequence[Tensor], codebooks: Sequence[Tensor], ch
     outs = [torch.empty((b, c, h, w), dtype=torch.int64, device=dev) for _ in zs]
     if b == 0 or h * w == 0:
         return outs
+    if zs[0].dtype == torch.bfloat16 and _bf16_via_fp32(b, dtot, h * w, c, d, k, chan_stride):
+        zs = [z.float() for z in zs]
+        es = [e.to(torch.bfloat16).float() for e in es]
     sp = _lib.stream_ptr(dev)
     ws = _lib.workspace(dev, sp, c, k, d)
     rc = _lib.lib().ctvq_argmin(_lib.ptr_array(zs), len(zs), _lib.ptr_array(es), b, dtot, h * w, c, d, k, chan_stride,
@@ -101,6 +114,10 @@ class _Quantize(torch.autograd.Function):
             ctx.set_materialize_grads(False)
             return torch.empty((b, c * d, h, w), dtype=io_dtype, device=dev), nan, empty_inds, per
         ctx.empty = False
+        ctx.cast = io_dtype == torch.bfloat16 and _bf16_via_fp32(b, dtot, h * w, c, d, k, chan_stride)
+        if ctx.cast:
+            z = z.float()
+            es = [e.to(torch.bfloat16).float() for e in es]
         dt = _dtype_code(z)
         out = torch.empty((b, c * d, h, w), dtype=z.dtype, device=dev)
         losses = torch.empty(c + 1, dtype=torch.float32, device=dev)
@@ -126,6 +143,8 @@ class _Quantize(torch.autograd.Function):
         ctx.save_for_backward(z, inds, *es)
         ctx.meta = (float(beta), int(chan_stride), b, dtot, h, w, c, d, k, comm)
         ctx.io_dtype = io_dtype
+        if ctx.cast:
+            out = out.to(torch.bfloat16)
         per = losses[:c]
         ctx.mark_non_differentiable(inds, per)
         ctx.set_materialize_grads(False)  # unused outputs arrive as None: no zero-fill kernels, no host sync
@@ -175,6 +194,8 @@ class _Quantize(torch.autograd.Function):
         _lib.maybe_validate(ws, dev, sp, "quantiser backward")
         if comm is not None:
             ge = comm.allreduce_(ge)  # the one collective of the path (NCCL), on the backward kernel's stream
+        if gz.dtype != ctx.io_dtype:
+            gz = gz.to(ctx.io_dtype)
         return (gz, None, None, None, None, None, *ge.unbind(0))
 
 

@@ -42,7 +42,7 @@ def time_ms(fn, iters, flush):
     return ts[len(ts) // 2]
 
 
-def point(N, D, K, C, HW, kind, dev, flush):
+def point(N, D, K, C, HW, kind, dev, flush, dtype=torch.float32):
     d = D // C
     B = N // HW
     torch.manual_seed(0)
@@ -52,13 +52,14 @@ def point(N, D, K, C, HW, kind, dev, flush):
         for e in books:
             e.data = torch.randn(K, d, device=dev) * 0.5
     side = int(HW ** 0.5)
-    z = torch.randn(B, D, side, side, device=dev).requires_grad_(True)
-    g_out = torch.randn(B, C * d, side, side, device=dev)
+    z = torch.randn(B, D, side, side, device=dev).to(dtype).requires_grad_(True)
+    g_out = torch.randn(B, C * d, side, side, device=dev).to(dtype)
     g_loss = torch.ones((), device=dev)
     used = min(D, (C - 1) + d)
-    fb = 4 * used + 4 * C * d + 8 * C
-    bb = 4 * C * d + 4 * used + 8 * C + 4 * D
-    small = N * D * 4 < 200e6
+    es = 2 if dtype == torch.bfloat16 else 4   # bytes per latent / output / gradient element (indices stay int64)
+    fb = es * used + es * C * d + 8 * C
+    bb = es * C * d + es * used + 8 * C + es * D
+    small = N * D * es < 200e6
     fl = flush if small else None
 
     def fwd():
@@ -79,9 +80,9 @@ def point(N, D, K, C, HW, kind, dev, flush):
     # parity sample vs the C oracle (exact)
     with torch.no_grad():
         _, _, inds = m(z[: max(1, 4096 // HW)], inds=True)
-    ref = CO.argmin(z[: max(1, 4096 // HW)].detach().cpu(), [e.detach().cpu() for e in books])
+    ref = CO.argmin(z[: max(1, 4096 // HW)].detach().float().cpu(), [e.detach().to(dtype).float().cpu() for e in books])
     ok = bool(torch.equal(inds.cpu().reshape(ref.shape), ref))
-    return dict(N=N, D=D, K=K, C=C, HW=HW, codebook=kind, path=path, fwd_ms=t_f, fwdbwd_ms=t_fb,
+    return dict(N=N, D=D, K=K, C=C, HW=HW, codebook=kind, dtype="bf16" if dtype == torch.bfloat16 else "fp32", path=path, fwd_ms=t_f, fwdbwd_ms=t_fb,
                 fwd_Mlat_s=N / t_f / 1e3, fwdbwd_Mlat_s=N / t_fb / 1e3, fwd_gbs=fb * N / t_f / 1e6,
                 fwd_frac=fb * N / t_f / 1e6 / PEAK, fwd_tflops=2.0 * N * K * d * C / t_f / 1e9, fwdbwd_gbs=(fb + bb) * N / t_fb / 1e6,
                 fwdbwd_frac=(fb + bb) * N / t_fb / 1e6 / PEAK, idx_exact=ok)
@@ -89,7 +90,7 @@ def point(N, D, K, C, HW, kind, dev, flush):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_sweep.md"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_sweep.md"))
     ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -104,15 +105,19 @@ def main():
         (1 << 20, 64, 256, 1, 256, "trained"), (1 << 20, 128, 256, 1, 256, "trained"), (1 << 18, 256, 256, 1, 256, "trained"),
         (1 << 20, 64, 1024, 1, 256, "trained"), (1 << 18, 128, 4096, 1, 256, "trained"), (1 << 16, 256, 16384, 1, 256, "trained"),
         (1 << 20, 32, 16384, 1, 256, "trained"),
+        # neighbours of the MCQ shape (two codebooks; 128x128 images) and bf16 latents (dtype = CTVQ_BF16)
+        (1 << 20, 64, 64, 2, 64, "trained"), (1 << 20, 128, 64, 4, 256, "trained"),
+        (1 << 20, 128, 64, 4, 64, "trained", torch.bfloat16), (1 << 20, 128, 64, 1, 64, "trained", torch.bfloat16),
+        (1 << 20, 64, 512, 1, 256, "init", torch.bfloat16),
     ]
     if not args.quick:
         pts += [(1 << 24, 32, 256, 1, 256, "trained")]
     rows = []
     for pt in pts:
         try:
-            r = point(*pt, dev, flush)
+            r = point(*pt[:6], dev, flush, *(pt[6:]))
         except RuntimeError as e:
-            r = dict(N=pt[0], D=pt[1], K=pt[2], C=pt[3], HW=pt[4], codebook=pt[5], error=str(e)[:80])
+            r = dict(N=pt[0], D=pt[1], K=pt[2], C=pt[3], HW=pt[4], codebook=pt[5], dtype="?", error=str(e)[:80])
         rows.append(r)
         print(json.dumps(r), flush=True)
     # config 5: reparam + KL
@@ -166,18 +171,19 @@ def main():
         ct.append(r)
         print(json.dumps(r), flush=True)
     with open(args.out, "w") as f:
-        f.write("# round 1 — quantiser microbenchmark sweep (BASELINE.json configs[3]) and Gaussian branch (configs[4])\n\n")
+        f.write("# round 2 — quantiser microbenchmark sweep (BASELINE.json configs[3]) and Gaussian branch (configs[4])\n\n")
         f.write(f"One B200, fp32, CUDA-event median, HBM peak {PEAK:.0f} GB/s (MEASURED_PEAKS.json). `frac` = algorithmic bytes ÷ time ÷ peak "
                 "(HBM roofline). `fwd TF/s` = 2*K*D flops per row / time: the points with K >= 1024 are TENSOR-bound (tf32 peak taken as "
                 "half the measured bf16 burst peak of 1670 TF/s, i.e. 835 TF/s) and run the streaming tcgen05 kernel. "
-                "`idx_exact` = indices equal to the C oracle on a 4096-row sample.\n\n")
-        f.write("| N | D | K | C | HW | codebook | path | fwd ms | fwd M lat/s | fwd GB/s | fwd frac | fwd TF/s | fwd+bwd ms | fwd+bwd M lat/s | fwd+bwd GB/s | fwd+bwd frac | idx_exact |\n")
-        f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+                "`idx_exact` = indices equal to the C oracle on a 4096-row sample.  bf16 rows: latents / outputs / gradients are bf16 (dtype = CTVQ_BF16), "
+                "the algorithmic bytes are counted at 2 bytes per element.\n\n")
+        f.write("| N | D | K | C | HW | codebook | dtype | path | fwd ms | fwd M lat/s | fwd GB/s | fwd frac | fwd TF/s | fwd+bwd ms | fwd+bwd M lat/s | fwd+bwd GB/s | fwd+bwd frac | idx_exact |\n")
+        f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         for r in rows:
             if "error" in r:
                 f.write(f"| {r['N']} | {r['D']} | {r['K']} | {r['C']} | {r['HW']} | {r['codebook']} | error: {r['error']} |\n")
                 continue
-            f.write(f"| {r['N']} | {r['D']} | {r['K']} | {r['C']} | {r['HW']} | {r['codebook']} | {r['path']} | {r['fwd_ms']:.4f} | "
+            f.write(f"| {r['N']} | {r['D']} | {r['K']} | {r['C']} | {r['HW']} | {r['codebook']} | {r['dtype']} | {r['path']} | {r['fwd_ms']:.4f} | "
                     f"{r['fwd_Mlat_s']:.1f} | {r['fwd_gbs']:.0f} | {r['fwd_frac']:.3f} | {r['fwd_tflops']:.0f} | {r['fwdbwd_ms']:.4f} | {r['fwdbwd_Mlat_s']:.1f} | "
                     f"{r['fwdbwd_gbs']:.0f} | {r['fwdbwd_frac']:.3f} | {r['idx_exact']} |\n")
         f.write("\n## reparameterise + KL (16 B/element forward: mu, logvar, eps in, z out; backward +24 B)\n\n")
