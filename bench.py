@@ -584,7 +584,12 @@ def main():
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
-    # per-kernel durations (events on the launching stream = torch's current stream), >= 100 ms of load per quantity
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    # per-kernel durations (events on the launching stream = torch's current stream), >= 100 ms of load per quantity.
+    # `reps` comes from the MAX-reduced time: every rank must run the same number of backward passes (= collectives)
     reps = max(args.steps, int(math.ceil(100.0 / max(ms / args.steps, 1e-3))))
     fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
@@ -605,10 +610,6 @@ def main():
     bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in bwd_ev)
     fwd_path = _lib.last_path()
 
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t)
     rows_per_gpu = B * H * W
     value = rows_per_gpu * world * args.steps / (ms * 1e-3)
 

@@ -11,7 +11,7 @@
 // All address arithmetic folds into immediates; the accumulator is flushed once per (persistent) CTA.
 #include <stdlib.h>
 
-#include "ctvq_common.cuh"
+#include "ctvq_tc_ptx.cuh"
 
 namespace ctvq {
 namespace {
@@ -261,11 +261,12 @@ constexpr int kBT4 = 384;
 // T: element type of z / g_out / grad_z (float, or __nv_bfloat16 for dtype = CTVQ_BF16: half the streamed bytes; codebook
 // values are rounded to bf16 as they are staged, all arithmetic stays fp32)
 template <int D, int C, int K, int HWT, int DTOT, int CS, typename T>
-__global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, const int ntiles) {
+__global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, const int ntiles, const __grid_constant__ CUtensorMap gomap) {
     const T* __restrict__ zT = reinterpret_cast<const T*>(p.z);
     const T* __restrict__ goT = reinterpret_cast<const T*>(p.g_out);
     T* __restrict__ gzT = reinterpret_cast<T*>(p.gz);
-    constexpr int TM = HWT;                 // rows per tile = one image
+    constexpr int TM = 64;                  // rows per tile: one 64-position segment of an image (the whole image at H*W = 64)
+    constexpr int SEG = HWT / TM;           // tiles per image
     constexpr int NST = 3;                  // g_out ring depth
     constexpr int USED = (C - 1) * CS + D;
     constexpr int ZS = TM + 1;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
     constexpr int NGZ = 4;                  // gz warps (8..11)
     constexpr int NACC = 8;                 // acc warps: 2 per accumulator slab (row halves, private copies)
     constexpr int kFull = 1, kEmpty = 3, kAcc = 5;
-    static_assert(ITEMS <= 4 && TM == 64, "configs' shapes");
+    static_assert(ITEMS <= 4 && HWT % TM == 0, "configs' shapes");
     extern __shared__ __align__(128) float smem[];
     T* go_s = reinterpret_cast<T*>(smem);                 // [NST][C*D][TM] in the I/O element type
     int* idx_s = reinterpret_cast<int*>(smem + NST * GOF * sizeof(T) / sizeof(float));  // [2][C][TM]
@@ -312,32 +313,43 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
         long long kreg[NI];
         const int m = tid & (TM - 1), half = tid / TM;  // thread stages row m, channels / codebooks congruent to `half` mod 4
         auto prefetch = [&](int it) {
-            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;  // tile = image
+            const long long t = (long long)blockIdx.x + (long long)it * gridDim.x;  // tile = (image, segment)
+            const long long b = t / SEG;
+            const int r0 = (int)(t - b * SEG) * TM;
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
                 const int c = half + 4 * i;
-                kreg[i] = (c < C) ? __ldg(p.idx + ((size_t)b * C + c) * HWT + m) : 0;
+                kreg[i] = (c < C) ? __ldg(p.idx + ((size_t)b * C + c) * HWT + r0 + m) : 0;
             }
-            const T* src = zT + (size_t)b * DTOT * HWT + m;
+            const T* src = zT + (size_t)b * DTOT * HWT + r0 + m;
 #pragma unroll
             for (int i = 0; i < NZ; ++i) {
                 const int ch = half + 4 * i;
                 zreg[i] = (ch < USED) ? IO<T>::ld(src + (size_t)ch * HWT) : 0.0f;
             }
         };
-        auto issue_go = [&](int it) {  // thread 0: stream image it's g_out block into ring slot it % NST
+        auto issue_go = [&](int it) {  // warp 0: stream tile it's g_out block into ring slot it % NST
             const int st = it % NST;
             if (it >= NST) mbar_wait(bar_empty + 8 * st, (uint32_t)((it / NST) - 1) & 1u);
-            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
-            mbar_expect_tx(bar_full + 8 * st, GOF * (uint32_t)sizeof(T));
-            bulk_g2s(smem_u32(go_s + st * GOF), goT + (size_t)b * GOF, GOF * (uint32_t)sizeof(T), bar_full + 8 * st);
+            const long long t = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long b = t / SEG;
+            const int r0 = (int)(t - b * SEG) * TM;
+            if (lane == 0) mbar_expect_tx(bar_full + 8 * st, GOF * (uint32_t)sizeof(T));
+            __syncwarp();
+            if (SEG == 1) {  // the image's whole g_out block is contiguous in NCHW: one bulk copy
+                if (lane == 0) bulk_g2s(smem_u32(go_s + st * GOF), goT + (size_t)b * GOF, GOF * (uint32_t)sizeof(T), bar_full + 8 * st);
+            } else {         // one 64-position run per channel: ONE 3-D tensor-map box [C*D][64] (a bulk copy per channel measured
+                             // ~46 cycles of TMA service each -- 3 us per tile at 128 channels)
+                if (lane == 0) tc::tma_load_3d(smem_u32(go_s + st * GOF), &gomap, bar_full + 8 * st, r0, 0, (int)b);
+            }
+            __syncwarp();
         };
         if (niter > 0) prefetch(0);
-        if (tid == 0 && has_go)
+        if (warp == 0 && has_go)
             for (int it = 0; it < NST - 1 && it < niter; ++it) issue_go(it);
         for (int it = 0; it < niter; ++it) {
             const int buf = it & 1;
-            if (tid == 0 && has_go && it + NST - 1 < niter) issue_go(it + NST - 1);
+            if (warp == 0 && has_go && it + NST - 1 < niter) issue_go(it + NST - 1);
             if (it >= 2) named_sync(kEmpty + buf, kBT4 - 0);  // gz warps finished reading this z/idx slot (iteration it-2)
             int* idb = idx_s + buf * C * TM;
             float* zb = zs + buf * USED * ZS;
@@ -404,11 +416,12 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
         const int m = (lane & 15) * 4;           // rows m..m+3
         for (int it = 0; it < niter; ++it) {
             const int buf = it & 1, st = it % NST;
-            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long t = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long b = t / SEG;
             const int* idb = idx_s + buf * C * TM;
             const float* zb = zs + buf * USED * ZS;
             const T* gos = go_s + st * GOF;
-            T* gz_row = gzT + (size_t)b * DTOT * HWT + m;
+            T* gz_row = gzT + (size_t)b * DTOT * HWT + (int)(t - b * SEG) * TM + m;
             // zero channels first: they depend on nothing
             const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
             for (int ch = USED + 2 * gw + hsel; ch < DTOT; ch += 2 * NGZ) IO<T>::st4(gz_row + (size_t)ch * HWT, zero4);
@@ -454,19 +467,27 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
 template <int D, int C, int K, int HWT, int DTOT, int CS, typename T>
 int launch_tma(const BwdParams& p, cudaStream_t s) {
     constexpr int USED = (C - 1) * CS + D;
-    constexpr size_t smem = sizeof(T) * 3 * (size_t)C * D * HWT +
-                            sizeof(float) * (2 * (size_t)C * HWT + 2 * (size_t)USED * (HWT + 1) +
+    constexpr int TM = 64;
+    constexpr size_t smem = sizeof(T) * 3 * (size_t)C * D * TM +
+                            sizeof(float) * (2 * (size_t)C * TM + 2 * (size_t)USED * (TM + 1) +
                                              2 * (size_t)C * K * D + (((size_t)C * K * (D + 1) + 1) & ~(size_t)1)) + 6 * 8;
     static_assert(smem <= 227 * 1024, "shared memory");
     if (p.N % HWT != 0) return CTVQ_E_UNSUPPORTED;
-    const long long nt = p.N / HWT;  // one image per tile
+    const long long nt = p.N / TM;  // one 64-position segment of an image per tile
     if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
     int grid = sm_count();
     if (grid > nt) grid = (int)nt;
+    CUtensorMap gomap;
+    memset(&gomap, 0, sizeof(gomap));
+    if (HWT != TM && p.g_out != nullptr) {
+        if (p.B > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
+        const int rc = tc::make_plain_map(gomap, p.g_out, IO<T>::kDtype, HWT, (long long)C * D, p.B, TM, C * D);
+        if (rc != CTVQ_OK) return rc;
+    }
     auto kern = vq_bwd_tma_kernel<D, C, K, HWT, DTOT, CS, T>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, kBT4, smem, s>>>(p, (int)nt);
+    kern<<<grid, kBT4, smem, s>>>(p, (int)nt, gomap);
     return (int)cudaGetLastError();
 }
 
@@ -655,6 +676,13 @@ int launch_backward_fast(const BwdParams& p, cudaStream_t s) {
         const bool go_ok = p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0;
         if (go_ok && p.N >= (long long)sm_count() * 64 * 4 && !no_tma) return launch_tma<32, 4, 64, 64, 128, 1, float>(p, s);
         return launch<32, 4, 64, 64, 128, 1, 2>(p, s);
+    }
+    // neighbours of that shape (same kernel, one 64-position segment per tile): 128x128 images (H*W = 256) and two codebooks
+    if (p.d == 32 && p.K == 64 && p.cs == 1 && (p.HW == 64 || p.HW == 256) && ((p.C == 4 && p.Dtot == 128) || (p.C == 2 && p.Dtot == 64)) &&
+        (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0) && p.N >= (long long)sm_count() * 64 * 4 && !no_tma) {
+        if (p.C == 4) return launch_tma<32, 4, 64, 256, 128, 1, float>(p, s);
+        if (p.HW == 64) return launch_tma<32, 2, 64, 64, 64, 1, float>(p, s);
+        return launch_tma<32, 2, 64, 256, 64, 1, float>(p, s);
     }
     // configs/ct_mcq_vae.yaml: C=1, d=128, K=64, latents [B,128,8,8]
     if (p.d == 128 && p.C == 1 && p.K == 64 && p.HW == 64 && p.Dtot == 128) {

@@ -1,0 +1,351 @@
+// Single-codebook backward for codebooks of MANY codes whose [K, D] accumulator still fits in shared memory:
+// VectorQuantizer of configs/vq_vae.yaml (K=512, D=64) and the config-4 sweep shapes with K*D <= 32768.
+// Replaces autograd through models/vq_vae.py:43-53 (one_hot^T @ (q - z), the straight-through and commitment terms).
+//
+// vq_bwd_c1_kernel (ctvq_bwd_c1.cu) runs this shape as "stage a tile, barrier, accumulate, barrier, grad_z" with
+// global fp32 atomics per (row, channel) and reaches 30 % of the HBM roofline (round-2 ncu: issue active 39 %, every
+// phase waits for the slowest load of the previous one).  Here one persistent CTA per SM keeps the WHOLE [K, D]
+// accumulator in shared memory (128 KB at config 1) and nothing on the tile loop's critical path touches HBM:
+//   * 8 "worker" warps stage z with 8-byte cp.async copies into a padded [D][66] tile, THREE buffers, two tiles ahead
+//     (completion on an mbarrier); the tile's indices ride one tile ahead in a register and are range-checked once;
+//   * the same warps turn the tile into q - z IN PLACE: lanes along the channel, 8 rows x D/32 chunks of coalesced
+//     128-byte codebook reads from L2 in flight per lane (the codebook does not fit beside the accumulator);
+//   * 4 "acc" warps add q - z into the accumulator with plain read-modify-write: each owns (32-channel chunk, code
+//     residue class k mod R), so no two warps ever touch the same word -- race-free without atomics (fp32 shared
+//     atomics are a compare-and-swap loop on sm_100a); the residue test is warp-uniform;
+//   * the worker warps then compute grad_z = g_out - coef_z (q - z) from shared memory only: g_out streams through a
+//     cp.async.bulk (TMA) ring, one 256-byte run per channel, issued by a whole warp; 128-bit stores.
+// Tiles are 64 consecutive positions of one image (H*W % 64 == 0).  One red.global.add flush per CTA, then the
+// fused peer all-reduce tail (ctvq_peer.cuh) like every other backward kernel.
+#include <string.h>
+
+#include "ctvq_tc_ptx.cuh"
+
+namespace ctvq {
+namespace {
+
+constexpr int kRingThreads = 384;
+constexpr int kNW = 8;             // worker warps
+constexpr int kNAcc = 4;           // acc warps
+constexpr int kTMr = 64;           // rows per tile
+constexpr int kZS = kTMr + 2;      // padded row stride (8-byte aligned rows for 8-byte cp.async; 2-way bank conflicts with lanes along channels)
+
+__device__ __forceinline__ void nb_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {  // hinted wait, ~2 s bound then trap
+    for (int it = 0; it < 2048; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// D: channels (32 or 64); NST: g_out ring depth.  K and H*W are run-time (K * D floats of accumulator, H*W % 64 == 0).
+// seg_shift: log2(tiles per image) when that is a power of two, else -1.
+template <int D, int NST>
+__global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const BwdParams p, const int ntiles, const int seg_shift,
+                                                                          const __grid_constant__ CUtensorMap gomap,
+                                                                          const __grid_constant__ CUtensorMap zmap) {
+    constexpr int JCH = D / 32;          // 32-channel chunks
+    constexpr int R = kNAcc / JCH;       // code residue classes per chunk (acc warp = (chunk, k mod R))
+    constexpr int GOF = D * kTMr;        // floats per g_out stage
+    constexpr int NZB = 3;               // z / index buffers
+    constexpr int kDiff = 1, kAccDone = 4, kWork = 7;  // named barriers: kDiff + b, kAccDone + b (b = buffer), kWork
+    constexpr int kBoth = (kNW + kNAcc) * 32;
+    static_assert(D == 32 || D == 64, "one or two channel chunks");
+    static_assert((R & (R - 1)) == 0 && R >= 1, "residue classes");
+    extern __shared__ __align__(128) float smem[];
+    const int K = p.K, HW = p.HW;
+    const int KD = K * D;
+    float* go_s = smem;                                              // [NST][D][64]
+    float* zs = go_s + NST * GOF;                                    // [NZB][D][66]: z, then q - z in place
+    int* idx_s = reinterpret_cast<int*>(zs + NZB * D * kZS);         // [NZB][64] range-checked indices
+    unsigned short* list_s = reinterpret_cast<unsigned short*>(idx_s + NZB * kTMr);  // [kNAcc][64] per-acc-warp row lists
+    uint64_t* bars = reinterpret_cast<uint64_t*>(list_s + kNAcc * kTMr);  // full[NST], empty[NST], zfull[NZB]
+    float* acc = reinterpret_cast<float*>(bars + 2 * NST + NZB + 1);  // [K][D]
+    const uint32_t bar_full = s_u32(&bars[0]), bar_empty = s_u32(&bars[NST]), bar_zfull = s_u32(&bars[2 * NST]);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { mb_init(bar_full + 8 * i, 1); mb_init(bar_empty + 8 * i, kNW); }
+        for (int i = 0; i < NZB; ++i) mb_init(bar_zfull + 8 * i, kNW * 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < KD / 4; i += kRingThreads) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float gl = __ldg(p.g_loss);
+    const double nd = (double)p.N * (double)D;
+    const float coef_e = (float)(2.0 / nd) * gl;
+    const float coef_z = (float)(2.0 * (double)p.beta / nd) * gl;
+    const float* __restrict__ E = p.E[0];
+    __syncthreads();
+    const int niter = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool has_go = p.g_out != nullptr;
+    const unsigned seg = (unsigned)(HW / kTMr);  // tiles per image
+    auto tile_base = [&](int it, unsigned& b, int& r0) {  // 32-bit: ntiles < 2^31
+        const unsigned t = blockIdx.x + (unsigned)it * gridDim.x;
+        b = seg_shift >= 0 ? (t >> seg_shift) : (t / seg);
+        r0 = (int)(t - b * seg) * kTMr;
+    };
+
+    if (warp >= kNW) {
+        // =========================== acc warps: (chunk, residue class) of the accumulator ===========================
+        const int aw = warp - kNW, jc = aw / R, res = aw % R;
+        float* ac = acc + jc * 32 + lane;
+        unsigned short* lst = list_s + aw * kTMr;  // this warp's rows of the tile, compacted: (code << 6) | row
+        const unsigned lt = (1u << lane) - 1u;
+        for (int it = 0; it < niter; ++it) {
+            const int zb = it % NZB;
+            nb_sync(kDiff + zb, kBoth);  // q - z of this tile is in place
+            const float* dcol = zs + (size_t)zb * D * kZS + (jc * 32 + lane) * kZS;
+            const int* ks = idx_s + zb * kTMr;
+            // ---- the tile's rows whose code falls in this warp's residue class, compacted into a list (ballot + prefix
+            // popcount, no serial find-first-set chain): the update loop below is warp-uniform, runs over this class's rows
+            // only, and reads four (code, row) pairs with ONE broadcast 64-bit load
+            int n = 0;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int kmine = ks[32 * hf + lane];
+                const bool mine = (kmine & (R - 1)) == res;
+                const unsigned mask = __ballot_sync(0xffffffffu, mine);
+                if (mine) lst[n + __popc(mask & lt)] = (unsigned short)((kmine << 6) | (32 * hf + lane));
+                n += __popc(mask);
+            }
+            __syncwarp();
+            struct Group { int k[4]; float d[4]; };
+            auto fetch = [&](int i, Group& g) {  // entries i..i+3: codes and q - z of the lane's channel
+                const uint2 pk = *reinterpret_cast<const uint2*>(lst + i);
+                const unsigned e0 = pk.x & 0xffffu, e1 = pk.x >> 16, e2 = pk.y & 0xffffu, e3 = pk.y >> 16;
+                g.k[0] = (int)(e0 >> 6); g.k[1] = (int)(e1 >> 6); g.k[2] = (int)(e2 >> 6); g.k[3] = (int)(e3 >> 6);
+                g.d[0] = dcol[e0 & 63u]; g.d[1] = dcol[e1 & 63u]; g.d[2] = dcol[e2 & 63u]; g.d[3] = dcol[e3 & 63u];
+            };
+            auto rmw = [&](const Group& g) {
+                const bool distinct = g.k[0] != g.k[1] && g.k[0] != g.k[2] && g.k[0] != g.k[3] && g.k[1] != g.k[2] &&
+                                      g.k[1] != g.k[3] && g.k[2] != g.k[3];
+                if (distinct) {  // four different words: loads first, then stores
+                    const float a0 = ac[g.k[0] * D], a1 = ac[g.k[1] * D], a2 = ac[g.k[2] * D], a3 = ac[g.k[3] * D];
+                    ac[g.k[0] * D] = a0 + g.d[0]; ac[g.k[1] * D] = a1 + g.d[1]; ac[g.k[2] * D] = a2 + g.d[2]; ac[g.k[3] * D] = a3 + g.d[3];
+                } else {
+                    ac[g.k[0] * D] += g.d[0]; ac[g.k[1] * D] += g.d[1]; ac[g.k[2] * D] += g.d[2]; ac[g.k[3] * D] += g.d[3];
+                }
+            };
+            int i = 0;
+            if (n >= 4) {  // software pipeline: the next group's list entry and q - z loads fly under this group's update
+                Group cur, nxt;
+                fetch(0, cur);
+                for (i = 4; i + 4 <= n; i += 4) {
+                    fetch(i, nxt);
+                    rmw(cur);
+                    cur = nxt;
+                }
+                rmw(cur);
+            }
+            for (; i < n; ++i) {  // 0..3 left-over rows
+                const unsigned e = lst[i];
+                ac[(int)(e >> 6) * D] += dcol[e & 63u];
+            }
+            __syncwarp();  // the list is rewritten for the next tile
+            nb_arrive(kAccDone + zb, kBoth);
+        }
+    } else {
+        // =========================== worker warps: staging, q - z, grad_z ===========================================
+        const int gt = tid;                      // 0..255
+        const int hsel = lane >> 4;              // half-warp: which channel of the pair
+        const int m = (lane & 15) * 4;           // rows m..m+3 in the grad_z pass
+        constexpr int CPT = D * kTMr / 2 / (kNW * 32);  // 8-byte copies per thread per tile
+        // thread gt copies row pairs (gt & 31) of channels (gt >> 5) + 8 i: coalesced 256-byte runs along H*W
+        const uint32_t st_dst = s_u32(zs + (gt >> 5) * kZS + 2 * (gt & 31));
+        const size_t st_src = (size_t)(gt >> 5) * HW + 2 * (gt & 31);
+        long long kreg = 0;                      // index of row gt (gt < 64) of the most recently staged tile
+        auto stage = [&](int it) {               // tile it -> buffer it % NZB (asynchronous; completion arrives on zfull)
+            unsigned b;
+            int r0;
+            tile_base(it, b, r0);
+            const int zb = it % NZB;
+            const float* src = p.z + (size_t)b * D * HW + r0 + st_src;
+            const uint32_t dst = st_dst + (uint32_t)zb * D * kZS * 4u;
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)i * 8u * kZS * 4u), "l"(src) : "memory");
+                src += (size_t)8 * HW;
+            }
+            if (gt < kTMr) kreg = __ldg(p.idx + (size_t)b * HW + r0 + gt);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_zfull + 8 * zb) : "memory");
+        };
+        auto publish_idx = [&](int it) {         // the index loaded by stage(it): range-check, clamp, hand to everybody
+            if (gt < kTMr) {
+                long long kk = kreg;
+                if (kk < 0 || kk >= K) { atomicOr(p.err, 1u); kk = kk < 0 ? 0 : K - 1; }  // caller-supplied index out of range
+                idx_s[(it % NZB) * kTMr + gt] = (int)kk;
+            }
+        };
+        auto issue_go = [&](int it) {            // warp 0: stream tile it's g_out block [D][64] into ring slot it % NST
+            const int st = it % NST;
+            if (it >= NST) mb_wait(bar_empty + 8 * st, (uint32_t)((it / NST) - 1) & 1u);
+            unsigned b;
+            int r0;
+            tile_base(it, b, r0);
+            if (lane == 0) {  // ONE tensor-map box per tile (a 256-byte bulk copy per channel costs ~46 cycles of TMA service each)
+                mb_expect_tx(bar_full + 8 * st, GOF * 4u);
+                tc::tma_load_3d(s_u32(go_s + st * GOF), &gomap, bar_full + 8 * st, r0, 0, (int)b);
+            }
+            __syncwarp();
+        };
+        // this warp's 8 rows of tile `it`: wait for the staged tile, read the indices, issue the codebook reads -- 8 x D/32
+        // coalesced 128-byte rows from L2 per lane.  Called one tile AHEAD, so the L2 latency runs under the grad_z pass of
+        // the previous tile instead of stalling every warp at the top of the loop.
+        float e[8][JCH];
+        auto fetch_e = [&](int it) {
+            const int zb = it % NZB;
+            mb_wait(bar_zfull + 8 * zb, (uint32_t)(it / NZB) & 1u);
+            const int* ks = idx_s + zb * kTMr;
+            int k[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) k[u] = ks[warp + kNW * u];  // broadcast reads
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int c = 0; c < JCH; ++c) e[u][c] = __ldg(E + (size_t)k[u] * D + c * 32 + lane);
+        };
+        // HBM latency is hidden TWICE: every z tile is requested into L2 kL2 tiles ahead by ONE tensor-map prefetch (no
+        // shared-memory destination, so it costs no buffer), and staged from L2 two tiles ahead -- with three buffers the
+        // staging lead alone is one iteration, less than an HBM round trip under load
+        constexpr int kL2 = 5;
+        auto prefetch_z = [&](int it) {
+            unsigned b;
+            int r0;
+            tile_base(it, b, r0);
+            asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&zmap), "r"(r0), "r"(0), "r"((int)b) : "memory");
+            if (has_go)  // the g_out ring runs NST-1 tiles ahead: same double cover
+                asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&gomap), "r"(r0), "r"(0), "r"((int)b) : "memory");
+        };
+        if (tid == 0)
+            for (int it = 2; it < kL2 && it < niter; ++it) prefetch_z(it);
+        if (niter > 0) { stage(0); publish_idx(0); }
+        if (niter > 1) { stage(1); publish_idx(1); }
+        if (warp == 0 && has_go)
+            for (int it = 0; it < NST - 1 && it < niter; ++it) issue_go(it);
+        nb_sync(kWork, kNW * 32);                // the first tiles' indices are published
+        if (niter > 0) fetch_e(0);
+        for (int it = 0; it < niter; ++it) {
+            const int zb = it % NZB, st = it % NST;
+            if (warp == 0 && has_go && it + NST - 1 < niter) issue_go(it + NST - 1);
+            if (tid == 0 && it + kL2 < niter) prefetch_z(it + kL2);
+            if (it >= 1 && it + 1 < niter) publish_idx(it + 1);  // loaded by the refill of the previous iteration
+            // ---- q - z in place (the codebook values were requested one tile ago) ---------------------------------------
+            {
+                float* zt = zs + (size_t)zb * D * kZS;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int c = 0; c < JCH; ++c) {
+                        float* zp = zt + (c * 32 + lane) * kZS + warp + kNW * u;
+                        *zp = __fsub_rn(e[u][c], *zp);  // q - z
+                    }
+            }
+            nb_arrive(kDiff + zb, kBoth);        // the acc warps may start on this tile
+            nb_sync(kWork, kNW * 32);            // every worker's share of q - z is in place (and grad_z of tile it-1 is done)
+            // ---- refill: tile it+2 re-uses the buffer of tile it-1 (its grad_z is done; wait for its accumulation) ----
+            if (it >= 1) nb_sync(kAccDone + (it + 2) % NZB, kBoth);
+            if (it + 2 < niter) stage(it + 2);
+            if (it + 1 < niter) fetch_e(it + 1);  // next tile's codebook rows fly under this tile's grad_z
+            // ---- grad_z = g_out - coef_z (q - z): lanes along H*W, 128-bit ------------------------------------------------
+            unsigned b;
+            int r0;
+            tile_base(it, b, r0);
+            const float* zt = zs + (size_t)zb * D * kZS;
+            const float* gos = go_s + st * GOF;
+            float* gz_row = p.gz + (size_t)b * D * HW + r0 + m;
+            if (has_go) mb_wait(bar_full + 8 * st, (uint32_t)(it / NST) & 1u);
+#pragma unroll 4
+            for (int ch = 2 * warp + hsel; ch < D; ch += 2 * kNW) {
+                const float2 da = *reinterpret_cast<const float2*>(zt + ch * kZS + m), db = *reinterpret_cast<const float2*>(zt + ch * kZS + m + 2);
+                float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_go) go = *reinterpret_cast<const float4*>(gos + ch * kTMr + m);
+                *reinterpret_cast<float4*>(gz_row + (size_t)ch * HW) =
+                    make_float4(go.x - coef_z * da.x, go.y - coef_z * da.y, go.z - coef_z * db.x, go.w - coef_z * db.y);
+            }
+            __syncwarp();
+            if (lane == 0 && has_go) mb_arrive(bar_empty + 8 * st);  // ring slot may be refilled
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < KD; i += kRingThreads) {
+        const float v = acc[i];
+        if (v != 0.0f) atomicAdd(&p.gE[i], coef_e * v);
+    }
+    peer_tail(p.peer, p.gE);  // fused collective (no-op unless ctvq_backward_allreduce armed it)
+}
+
+template <int D>
+size_t ring_smem(int K, int nst) {
+    return ((size_t)nst * D * kTMr + 3 * (size_t)D * kZS) * 4 + 3 * kTMr * 4 + kNAcc * kTMr * 2 + (2 * (size_t)nst + 3 + 1) * 8 + (size_t)K * D * 4;
+}
+
+template <int D, int NST>
+int launch_ring(const BwdParams& p, cudaStream_t s) {
+    const size_t smem = ring_smem<D>(p.K, NST);
+    const long long nt = p.N / kTMr;
+    if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
+    int grid = sm_count();
+    if (grid > nt) grid = (int)nt;
+    CUtensorMap gomap;
+    memset(&gomap, 0, sizeof(gomap));
+    if (p.g_out != nullptr) {
+        if (p.B > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
+        const int rc = tc::make_plain_map(gomap, p.g_out, CTVQ_F32, p.HW, D, p.B, kTMr, D);
+        if (rc != CTVQ_OK) return rc;
+    }
+    CUtensorMap zmap;
+    if (p.B > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
+    if (tc::make_plain_map(zmap, p.z, CTVQ_F32, p.HW, D, p.B, kTMr, D) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
+    auto kern = vq_bwd_c1_ring_kernel<D, NST>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int seg = p.HW / kTMr;
+    int seg_shift = -1;
+    if ((seg & (seg - 1)) == 0)
+        for (seg_shift = 0; (1 << seg_shift) < seg; ++seg_shift) {}
+    kern<<<grid, kRingThreads, smem, s>>>(p, (int)nt, seg_shift, gomap, zmap);
+    return (int)cudaGetLastError();
+}
+}  // namespace
+
+// CTVQ_E_UNSUPPORTED: not a single full-width fp32 codebook of 32 / 64 channels, H*W not a multiple of 64, unaligned
+// tensors, an accumulator beyond shared memory, or a batch too small to amortise zeroing + flushing it per CTA.
+int launch_backward_ring(const BwdParams& p, cudaStream_t s) {
+    // d = 32 tiles (8 KB) are too small for the per-tile hand-overs: measured 0.188 vs 0.145 ms for vq_bwd_c1_kernel at K=256, 1 M rows
+    if (p.dtype != CTVQ_F32 || p.C != 1 || p.d != p.Dtot || p.d != 64 || p.HW % kTMr != 0) return CTVQ_E_UNSUPPORTED;
+    if (p.K < 128 || p.K > 1024 || (p.K * p.d) % 4 != 0) return CTVQ_E_UNSUPPORTED;  // few codes: the ownership kernels of ctvq_bwd_fast.cu / the tiled kernel
+    if ((reinterpret_cast<uintptr_t>(p.z) & 15) || (reinterpret_cast<uintptr_t>(p.gz) & 15) ||
+        (p.g_out && (reinterpret_cast<uintptr_t>(p.g_out) & 15)) || (reinterpret_cast<uintptr_t>(p.idx) & 7))
+        return CTVQ_E_UNSUPPORTED;
+    // every CTA zeroes and flushes a [K, d] accumulator: only worth it when the rows outweigh that
+    if (p.N < (long long)sm_count() * kTMr * 4 || p.N < (long long)sm_count() * p.K) return CTVQ_E_UNSUPPORTED;
+    const size_t cap = 227 * 1024;
+    if (p.d == 64) {
+        if (ring_smem<64>(p.K, 3) <= cap) return launch_ring<64, 3>(p, s);
+        if (ring_smem<64>(p.K, 2) <= cap) return launch_ring<64, 2>(p, s);
+    } else {
+        if (ring_smem<32>(p.K, 3) <= cap) return launch_ring<32, 3>(p, s);
+        if (ring_smem<32>(p.K, 2) <= cap) return launch_ring<32, 2>(p, s);
+    }
+    return CTVQ_E_UNSUPPORTED;
+}
+
+}  // namespace ctvq

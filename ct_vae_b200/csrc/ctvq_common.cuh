@@ -134,6 +134,7 @@ int launch_gather(const QuantParams& p, cudaStream_t s);
 int launch_backward(const BwdParams& p, cudaStream_t s);
 int launch_backward_fast(const BwdParams& p, cudaStream_t s);   // shape-specialised; CTVQ_E_UNSUPPORTED otherwise
 int launch_backward_c1(const BwdParams& p, cudaStream_t s);     // single full-width codebook, shared-atomic accumulator
+int launch_backward_ring(const BwdParams& p, cudaStream_t s);   // single codebook of many codes, [K,d] accumulator resident in shared memory, cp.async / TMA rings
 int launch_backward_tiled(const BwdParams& p, cudaStream_t s);  // CTVQ_E_UNSUPPORTED when [C,K,d] exceeds shared memory
 int launch_reparam_fwd(const float* mu, const float* lv, const float* eps, long long B, int L, float* z, float* kld,
                        Workspace* ws, cudaStream_t s);

@@ -463,6 +463,8 @@ int launch_backward(const BwdParams& p0, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     {
         int rc = CTVQ_E_UNSUPPORTED;
+        if (p.dtype == CTVQ_F32) rc = launch_backward_ring(p, s);  // one codebook of many codes, large batch: resident accumulator + rings
+        if (rc != CTVQ_E_UNSUPPORTED) return rc;
         if (p.dtype == CTVQ_F32) rc = launch_backward_c1(p, s);  // one full-width codebook at a batch that amortises a per-CTA accumulator
         if (rc != CTVQ_E_UNSUPPORTED) return rc;
         rc = launch_backward_fast(p, s);      // shape-specialised (configs' shapes), fp32 and bf16

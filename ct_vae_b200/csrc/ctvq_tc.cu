@@ -381,6 +381,19 @@ int make_maps(const QuantParams& p0, Maps& maps, int box_channels) {
     }
     return CTVQ_OK;
 }
+
+int make_plain_map(CUtensorMap& m, const void* base, int dtype, long long HW, long long CH, long long B, int box_hw, int box_ch) {
+    if (!encode_fn() || box_hw > 256 || box_ch > 256) return CTVQ_E_UNSUPPORTED;
+    const cuuint64_t es = dtype == CTVQ_BF16 ? 2 : 4;
+    const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)CH, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)HW * es, (cuuint64_t)HW * (cuuint64_t)CH * es};
+    const cuuint32_t box[3] = {(cuuint32_t)box_hw, (cuuint32_t)box_ch, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = encode_fn()(&m, dtype == CTVQ_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CTVQ_OK : CTVQ_E_UNSUPPORTED;
+}
 }  // namespace tc
 
 extern "C" void ctvq_debug_set_tc_dump(float* buf) { g_dbg = buf; }

@@ -190,6 +190,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn encode_fn();
 // 3-D tensor maps over the NCHW latents [B][Dtot][HW], box = 32 rows x box_channels (0: d), SWIZZLE_128B_ATOM_32B
 int make_maps(const QuantParams& p, Maps& maps, int box_channels);
+// un-swizzled 3-D tensor map over an NCHW tensor [B][CH][HW] of fp32 (CTVQ_F32) or bf16 (CTVQ_BF16) elements, box =
+// box_hw positions x box_ch channels of one image, landing dense [box_ch][box_hw] in shared memory (the backward kernels'
+// g_out rings: ONE TMA operation per tile instead of one small bulk copy per channel)
+int make_plain_map(CUtensorMap& m, const void* base, int dtype, long long HW, long long CH, long long B, int box_hw, int box_ch);
 
 }  // namespace tc
 }  // namespace ctvq

@@ -31,7 +31,10 @@ for l in sass:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         lines.append((cur, m.group(2).strip()))
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+ncu_cmd = ["ncu", "-i", rep, "--page", "source", "--csv"]
+if os.environ.get("NCU_K"):  # report holds several kernels: NCU_K=regex keeps one (and NCU_C=n takes n launches, default 1)
+    ncu_cmd += ["-k", "regex:" + os.environ["NCU_K"], "-c", os.environ.get("NCU_C", "1")]
+raw = subprocess.run(ncu_cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 H = next(r for r in rows if "Source" in r and "Instructions Executed" in r)
 st = rows.index(H) + 1
