@@ -4,17 +4,23 @@
 //
 // vq_bwd_c1_kernel (ctvq_bwd_c1.cu) runs this shape as "stage a tile, barrier, accumulate, barrier, grad_z" with
 // global fp32 atomics per (row, channel) and reaches 30 % of the HBM roofline (round-2 ncu: issue active 39 %, every
-// phase waits for the slowest load of the previous one).  Here one persistent CTA per SM keeps the WHOLE [K, D]
-// accumulator in shared memory (128 KB at config 1) and nothing on the tile loop's critical path touches HBM:
+// phase waits for the slowest load of the previous one): 0.328 ms at config 1, 1 M rows.  Here one persistent CTA per
+// SM keeps the WHOLE [K, D] accumulator in shared memory (128 KB at config 1) and nothing on the tile loop's critical
+// path waits for HBM (0.192 ms, 65 %):
 //   * 8 "worker" warps stage z with 8-byte cp.async copies into a padded [D][66] tile, THREE buffers, two tiles ahead
-//     (completion on an mbarrier); the tile's indices ride one tile ahead in a register and are range-checked once;
+//     (completion on an mbarrier) -- and every tile is requested into L2 five tiles ahead by ONE tensor-map prefetch, so the
+//     staging lead only has to cover L2 latency; the tile's indices ride one tile ahead in a register, range-checked once;
 //   * the same warps turn the tile into q - z IN PLACE: lanes along the channel, 8 rows x D/32 chunks of coalesced
-//     128-byte codebook reads from L2 in flight per lane (the codebook does not fit beside the accumulator);
-//   * 4 "acc" warps add q - z into the accumulator with plain read-modify-write: each owns (32-channel chunk, code
+//     128-byte codebook reads from L2 per lane (the codebook does not fit beside the accumulator), issued one tile
+//     ahead so they fly under the previous tile's grad_z pass;
+//   * 8 "acc" warps add q - z into the accumulator with plain read-modify-write: each owns (32-channel chunk, code
 //     residue class k mod R), so no two warps ever touch the same word -- race-free without atomics (fp32 shared
-//     atomics are a compare-and-swap loop on sm_100a); the residue test is warp-uniform;
+//     atomics are a compare-and-swap loop on sm_100a).  A warp compacts its class's rows into a list (ballot + prefix
+//     popcount; a find-first-set chain measured 3x slower), then walks it four rows at a time, software-pipelined two
+//     groups deep, loads before stores when the four codes differ;
 //   * the worker warps then compute grad_z = g_out - coef_z (q - z) from shared memory only: g_out streams through a
-//     cp.async.bulk (TMA) ring, one 256-byte run per channel, issued by a whole warp; 128-bit stores.
+//     TMA ring, ONE 3-D tensor-map box [D][64] per tile (a 256-byte bulk copy per channel costs ~46 cycles of TMA
+//     service each: measured 3 us per 128-channel tile); 128-bit stores.
 // Tiles are 64 consecutive positions of one image (H*W % 64 == 0).  One red.global.add flush per CTA, then the
 // fused peer all-reduce tail (ctvq_peer.cuh) like every other backward kernel.
 #include <string.h>
@@ -24,9 +30,9 @@
 namespace ctvq {
 namespace {
 
-constexpr int kRingThreads = 384;
+constexpr int kRingThreads = 512;
 constexpr int kNW = 8;             // worker warps
-constexpr int kNAcc = 4;           // acc warps
+constexpr int kNAcc = 8;           // acc warps (4: the workers waited on them a quarter of the time, round-2 ncu)
 constexpr int kTMr = 64;           // rows per tile
 constexpr int kZS = kTMr + 2;      // padded row stride (8-byte aligned rows for 8-byte cp.async; 2-way bank conflicts with lanes along channels)
 
@@ -128,8 +134,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
             }
             __syncwarp();
             struct Group { int k[4]; float d[4]; };
-            auto fetch = [&](int i, Group& g) {  // entries i..i+3: codes and q - z of the lane's channel
-                const uint2 pk = *reinterpret_cast<const uint2*>(lst + i);
+            auto unpack = [&](const uint2 pk, Group& g) {  // four (code, row) entries: codes and q - z of the lane's channel
                 const unsigned e0 = pk.x & 0xffffu, e1 = pk.x >> 16, e2 = pk.y & 0xffffu, e3 = pk.y >> 16;
                 g.k[0] = (int)(e0 >> 6); g.k[1] = (int)(e1 >> 6); g.k[2] = (int)(e2 >> 6); g.k[3] = (int)(e3 >> 6);
                 g.d[0] = dcol[e0 & 63u]; g.d[1] = dcol[e1 & 63u]; g.d[2] = dcol[e2 & 63u]; g.d[3] = dcol[e3 & 63u];
@@ -145,15 +150,23 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
                 }
             };
             int i = 0;
-            if (n >= 4) {  // software pipeline: the next group's list entry and q - z loads fly under this group's update
+            if (n >= 4) {
+                // software pipeline, two deep: the list entry of group g+2 and the q - z loads of group g+1 fly under the
+                // read-modify-write of group g (every shared-memory round trip but the accumulator's own is covered)
+                const uint2* l2 = reinterpret_cast<const uint2*>(lst);
+                const int ng = n >> 2;
                 Group cur, nxt;
-                fetch(0, cur);
-                for (i = 4; i + 4 <= n; i += 4) {
-                    fetch(i, nxt);
+                uint2 pk = l2[ng > 1 ? 1 : 0];
+                unpack(l2[0], cur);
+                for (int g = 1; g < ng; ++g) {
+                    const uint2 pk2 = l2[g + 1 < ng ? g + 1 : g];
+                    unpack(pk, nxt);
                     rmw(cur);
                     cur = nxt;
+                    pk = pk2;
                 }
                 rmw(cur);
+                i = ng << 2;
             }
             for (; i < n; ++i) {  // 0..3 left-over rows
                 const unsigned e = lst[i];
