@@ -665,9 +665,12 @@ int launch_backward_fast(const BwdParams& p, cudaStream_t s) {
     if (p.dtype == CTVQ_BF16) {
         // configs/mcq_vae.yaml shape with bf16 I/O: the TMA-ring kernel streams half the bytes
         const bool go16 = p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0;
-        if (p.d == 32 && p.C == 4 && p.K == 64 && p.HW == 64 && p.Dtot == 128 && p.cs == 1 && go16 && p.N % 64 == 0 &&
-            p.N >= (long long)sm_count() * 64 * 4 && (reinterpret_cast<uintptr_t>(p.gz) & 7) == 0)
-            return launch_tma<32, 4, 64, 64, 128, 1, __nv_bfloat16>(p, s);
+        if (p.d == 32 && p.K == 64 && p.cs == 1 && go16 && p.N % 64 == 0 && p.N >= (long long)sm_count() * 64 * 4 &&
+            (reinterpret_cast<uintptr_t>(p.gz) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.z) & 1) == 0) {
+            if (p.C == 4 && p.Dtot == 128 && p.HW == 64) return launch_tma<32, 4, 64, 64, 128, 1, __nv_bfloat16>(p, s);
+            if (p.C == 4 && p.Dtot == 128 && p.HW == 256) return launch_tma<32, 4, 64, 256, 128, 1, __nv_bfloat16>(p, s);
+            if (p.C == 2 && p.Dtot == 64 && p.HW == 64) return launch_tma<32, 2, 64, 64, 64, 1, __nv_bfloat16>(p, s);
+        }
         return CTVQ_E_UNSUPPORTED;  // the tiled kernel (ctvq_bwd.cu) carries bf16 for every other shape
     }
     static const bool no_tma = getenv("CTVQ_BWD_NO_TMA") != nullptr;  // A/B switch, read once per process

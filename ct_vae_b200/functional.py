@@ -41,7 +41,7 @@ def _bf16_via_fp32(b, dtot, hw, c, d, k, cs) -> bool:
     problems of any OTHER shape have no 16-bit tensor-core kernel yet: they are up-cast once and take the fp32 tcgen05
     kernels (bf16 values are exact in fp32 and the codebook is rounded first, so the result is the same contract), which is
     10x faster there than the generic bf16 kernels despite the two cast passes."""
-    native_shape = d == 32 and cs == 1 and k <= 64 and c == 4 and hw == 64 and dtot == 128
+    native_shape = d == 32 and cs == 1 and k <= 64 and ((c == 4 and dtot == 128 and hw in (64, 256)) or (c == 2 and dtot == 64 and hw == 64))
     return (not native_shape) and b * hw * c * k * d > (1 << 24)
 
 
