@@ -561,9 +561,18 @@ def main():
             torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(args.warmup):
+    # warm-up: the W steps the caller asked for, and then as many more as it takes to put >= 60 ms of load on the GPU
+    # (W = 3..5 steps are ~2 ms: SM clocks are still ramping from idle, peer mappings and instruction caches are cold, and
+    # at N = 8 the MAX over ranks of that start-up cost was 80 us per step of a 20-step timed region).  The extra count is
+    # a FIXED number derived from the workload size, identical on every rank (each step is a collective).
+    warm_extra = max(0, int(math.ceil(60.0 / max(B * H * W * 0.38e-6, 1e-3))) - args.warmup)
+    for _ in range(args.warmup + warm_extra):
         step(z)
     sync_all()
+    if world > 1:
+        # device-side rendezvous: dist.barrier() returns at different HOST times on different ranks; without this the rank
+        # that leaves first starts its clock first and then waits for the others inside its first collective
+        dist.all_reduce(torch.zeros(1, device=dev))
     small = B * D * H * W * 4 <= 200e6  # inputs do not exceed L2 (126 MB) comfortably: flush it between steps
     if small:
         flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -575,15 +584,25 @@ def main():
             b.record()
         sync_all()
         ms = sum(a.elapsed_time(b) for a, b in evs)
+        per = [a.elapsed_time(b) for a, b in evs]
+        step_ms = {"first": per[0], "median": statistics.median(per), "max": max(per)}
         del flush
     else:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
+        # ONE pair of events brackets the K steps (that is `ms`); the per-step marks in between only feed the diagnostic
+        # `step_ms` record (first / median / max step: start-up effects and rank skew show up there)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        # prime the launch queue: a ~0.5 ms spin kernel keeps the GPU busy while the host enqueues the first steps, so the
+        # clock starts on a GPU that has work queued behind it (otherwise the first step carries ~0.25 ms of host launch
+        # latency: 0.68 vs 0.42 ms measured at N = 8).  The spin is BEFORE the first event: not part of the timed region.
+        torch.cuda._sleep(1_000_000)
+        marks[0].record()
+        for i in range(args.steps):
             step(z)
-        e1.record()
+            marks[i + 1].record()
         sync_all()
-        ms = e0.elapsed_time(e1)
+        ms = marks[0].elapsed_time(marks[-1])
+        per = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
+        step_ms = {"first": per[0], "median": statistics.median(per), "max": max(per)}
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -729,11 +748,14 @@ def main():
     if rank == 0:
         fused = world > 1 and getattr(comm, "fuses_backward", False)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "step_ms": step_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(B, world), collective=(type(comm).__name__ if comm is not None else "none"),
                                schedule="one stream, program order: forward, backward" + (" (all-reduce fused in its last CTA)" if fused else (", all-reduce" if world > 1 else "")),
-                               numa=numa),
+                               numa=numa, warmup_steps_run=args.warmup + warm_extra,
+                               timing="K steps between two CUDA events on the launching stream, max over ranks; launch queue primed by "
+                                      "a spin kernel BEFORE the first event; warm-up = W steps + enough more for 60 ms of load"
+                                      + ("; device-side rendezvous (all-reduce) before the first event" if world > 1 else "")),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                         "what": "latents H2D from pinned memory; quantised output, int64 indices and loss D2H; forward + backward"},
