@@ -33,8 +33,6 @@ namespace {
 constexpr int kRingThreads = 512;
 constexpr int kNW = 8;             // worker warps
 constexpr int kNAcc = 8;           // acc warps (4: the workers waited on them a quarter of the time, round-2 ncu)
-constexpr int kTMr = 64;           // rows per tile
-constexpr int kZS = kTMr + 2;      // padded row stride (8-byte aligned rows for 8-byte cp.async; 2-way bank conflicts with lanes along channels)
 
 __device__ __forceinline__ void nb_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void nb_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -63,19 +61,24 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// D: channels (32 or 64); NST: g_out ring depth.  K and H*W are run-time (K * D floats of accumulator, H*W % 64 == 0).
+// D: channels (32 / 64 / 128); TMR: rows per tile (D * TMR = 4096 elements: 128 / 64 / 32); NST: g_out ring depth.
+// K and H*W are run-time (K * D floats of accumulator, H*W % TMR == 0).
 // seg_shift: log2(tiles per image) when that is a power of two, else -1.
-template <int D, int NST>
+template <int D, int TMR, int NST>
 __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const BwdParams p, const int ntiles, const int seg_shift,
                                                                           const __grid_constant__ CUtensorMap gomap,
                                                                           const __grid_constant__ CUtensorMap zmap) {
+    constexpr int kTMr = TMR;            // rows per tile
+    constexpr int kZS = TMR + 2;         // padded row stride (8-byte aligned rows for 8-byte cp.async; 2-way bank conflicts with lanes along channels)
+    constexpr int RB = TMR > 64 ? 7 : 6; // row bits of a list entry (code << RB | row, 16 bits)
+    constexpr unsigned RM = (1u << RB) - 1u;
     constexpr int JCH = D / 32;          // 32-channel chunks
     constexpr int R = kNAcc / JCH;       // code residue classes per chunk (acc warp = (chunk, k mod R))
     constexpr int GOF = D * kTMr;        // floats per g_out stage
     constexpr int NZB = 3;               // z / index buffers
     constexpr int kDiff = 1, kAccDone = 4, kWork = 7;  // named barriers: kDiff + b, kAccDone + b (b = buffer), kWork
     constexpr int kBoth = (kNW + kNAcc) * 32;
-    static_assert(D == 32 || D == 64, "one or two channel chunks");
+    static_assert((D == 32 || D == 64 || D == 128) && D * TMR == 4096, "16 KB tiles");
     static_assert((R & (R - 1)) == 0 && R >= 1, "residue classes");
     extern __shared__ __align__(128) float smem[];
     const int K = p.K, HW = p.HW;
@@ -125,19 +128,19 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
             // only, and reads four (code, row) pairs with ONE broadcast 64-bit load
             int n = 0;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
+            for (int hf = 0; hf < TMR / 32; ++hf) {
                 const int kmine = ks[32 * hf + lane];
                 const bool mine = (kmine & (R - 1)) == res;
                 const unsigned mask = __ballot_sync(0xffffffffu, mine);
-                if (mine) lst[n + __popc(mask & lt)] = (unsigned short)((kmine << 6) | (32 * hf + lane));
+                if (mine) lst[n + __popc(mask & lt)] = (unsigned short)((kmine << RB) | (32 * hf + lane));
                 n += __popc(mask);
             }
             __syncwarp();
             struct Group { int k[4]; float d[4]; };
             auto unpack = [&](const uint2 pk, Group& g) {  // four (code, row) entries: codes and q - z of the lane's channel
                 const unsigned e0 = pk.x & 0xffffu, e1 = pk.x >> 16, e2 = pk.y & 0xffffu, e3 = pk.y >> 16;
-                g.k[0] = (int)(e0 >> 6); g.k[1] = (int)(e1 >> 6); g.k[2] = (int)(e2 >> 6); g.k[3] = (int)(e3 >> 6);
-                g.d[0] = dcol[e0 & 63u]; g.d[1] = dcol[e1 & 63u]; g.d[2] = dcol[e2 & 63u]; g.d[3] = dcol[e3 & 63u];
+                g.k[0] = (int)(e0 >> RB); g.k[1] = (int)(e1 >> RB); g.k[2] = (int)(e2 >> RB); g.k[3] = (int)(e3 >> RB);
+                g.d[0] = dcol[e0 & RM]; g.d[1] = dcol[e1 & RM]; g.d[2] = dcol[e2 & RM]; g.d[3] = dcol[e3 & RM];
             };
             auto rmw = [&](const Group& g) {
                 const bool distinct = g.k[0] != g.k[1] && g.k[0] != g.k[2] && g.k[0] != g.k[3] && g.k[1] != g.k[2] &&
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
             }
             for (; i < n; ++i) {  // 0..3 left-over rows
                 const unsigned e = lst[i];
-                ac[(int)(e >> 6) * D] += dcol[e & 63u];
+                ac[(int)(e >> RB) * D] += dcol[e & RM];
             }
             __syncwarp();  // the list is rewritten for the next tile
             nb_arrive(kAccDone + zb, kBoth);
@@ -178,12 +181,17 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
     } else {
         // =========================== worker warps: staging, q - z, grad_z ===========================================
         const int gt = tid;                      // 0..255
-        const int hsel = lane >> 4;              // half-warp: which channel of the pair
-        const int m = (lane & 15) * 4;           // rows m..m+3 in the grad_z pass
-        constexpr int CPT = D * kTMr / 2 / (kNW * 32);  // 8-byte copies per thread per tile
-        // thread gt copies row pairs (gt & 31) of channels (gt >> 5) + 8 i: coalesced 256-byte runs along H*W
-        const uint32_t st_dst = s_u32(zs + (gt >> 5) * kZS + 2 * (gt & 31));
-        const size_t st_src = (size_t)(gt >> 5) * HW + 2 * (gt & 31);
+        constexpr int LQ = TMR / 4;              // grad_z pass: lanes per channel row (4 rows each), CPW channels per warp pass
+        constexpr int CPW = 32 / LQ;
+        const int hsel = lane / LQ;              // which channel of the warp's CPW
+        const int m = (lane % LQ) * 4;           // rows m..m+3 in the grad_z pass
+        constexpr int RPW = TMR / kNW;           // rows per worker warp in the q - z pass
+        constexpr int PP = TMR / 2;              // 8-byte row pairs per channel
+        constexpr int CST = kNW * 32 / PP;       // channels covered by one pass of the 256 staging threads
+        constexpr int CPT = D / CST;             // 8-byte copies per thread per tile
+        // thread gt copies row pair gt % PP of channels gt / PP + CST i: coalesced runs along H*W
+        const uint32_t st_dst = s_u32(zs + (gt / PP) * kZS + 2 * (gt % PP));
+        const size_t st_src = (size_t)(gt / PP) * HW + 2 * (gt % PP);
         long long kreg = 0;                      // index of row gt (gt < 64) of the most recently staged tile
         auto stage = [&](int it) {               // tile it -> buffer it % NZB (asynchronous; completion arrives on zfull)
             unsigned b;
@@ -194,8 +202,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
             const uint32_t dst = st_dst + (uint32_t)zb * D * kZS * 4u;
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)i * 8u * kZS * 4u), "l"(src) : "memory");
-                src += (size_t)8 * HW;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)i * CST * kZS * 4u), "l"(src) : "memory");
+                src += (size_t)CST * HW;
             }
             if (gt < kTMr) kreg = __ldg(p.idx + (size_t)b * HW + r0 + gt);
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_zfull + 8 * zb) : "memory");
@@ -219,19 +227,19 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
             }
             __syncwarp();
         };
-        // this warp's 8 rows of tile `it`: wait for the staged tile, read the indices, issue the codebook reads -- 8 x D/32
-        // coalesced 128-byte rows from L2 per lane.  Called one tile AHEAD, so the L2 latency runs under the grad_z pass of
+        // this warp's RPW rows of tile `it`: wait for the staged tile, read the indices, issue the codebook reads -- RPW x D/32
+        // (= 16) coalesced 128-byte rows from L2 per lane.  Called one tile AHEAD, so the L2 latency runs under the grad_z pass of
         // the previous tile instead of stalling every warp at the top of the loop.
-        float e[8][JCH];
+        float e[RPW][JCH];
         auto fetch_e = [&](int it) {
             const int zb = it % NZB;
             mb_wait(bar_zfull + 8 * zb, (uint32_t)(it / NZB) & 1u);
             const int* ks = idx_s + zb * kTMr;
-            int k[8];
+            int k[RPW];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) k[u] = ks[warp + kNW * u];  // broadcast reads
+            for (int u = 0; u < RPW; ++u) k[u] = ks[warp + kNW * u];  // broadcast reads
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < RPW; ++u)
 #pragma unroll
                 for (int c = 0; c < JCH; ++c) e[u][c] = __ldg(E + (size_t)k[u] * D + c * 32 + lane);
         };
@@ -264,7 +272,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
             {
                 float* zt = zs + (size_t)zb * D * kZS;
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int u = 0; u < RPW; ++u)
 #pragma unroll
                     for (int c = 0; c < JCH; ++c) {
                         float* zp = zt + (c * 32 + lane) * kZS + warp + kNW * u;
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
             float* gz_row = p.gz + (size_t)b * D * HW + r0 + m;
             if (has_go) mb_wait(bar_full + 8 * st, (uint32_t)(it / NST) & 1u);
 #pragma unroll 4
-            for (int ch = 2 * warp + hsel; ch < D; ch += 2 * kNW) {
+            for (int ch = CPW * warp + hsel; ch < D; ch += CPW * kNW) {
                 const float2 da = *reinterpret_cast<const float2*>(zt + ch * kZS + m), db = *reinterpret_cast<const float2*>(zt + ch * kZS + m + 2);
                 float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (has_go) go = *reinterpret_cast<const float4*>(gos + ch * kTMr + m);
@@ -305,59 +313,57 @@ __global__ void __launch_bounds__(kRingThreads, 1) vq_bwd_c1_ring_kernel(const B
     peer_tail(p.peer, p.gE);  // fused collective (no-op unless ctvq_backward_allreduce armed it)
 }
 
-template <int D>
+template <int D, int TMR>
 size_t ring_smem(int K, int nst) {
-    return ((size_t)nst * D * kTMr + 3 * (size_t)D * kZS) * 4 + 3 * kTMr * 4 + kNAcc * kTMr * 2 + (2 * (size_t)nst + 3 + 1) * 8 + (size_t)K * D * 4;
+    return ((size_t)nst * D * TMR + 3 * (size_t)D * (TMR + 2)) * 4 + 3 * TMR * 4 + kNAcc * TMR * 2 + (2 * (size_t)nst + 3 + 1) * 8 + (size_t)K * D * 4;
 }
 
-template <int D, int NST>
+template <int D, int TMR, int NST>
 int launch_ring(const BwdParams& p, cudaStream_t s) {
-    const size_t smem = ring_smem<D>(p.K, NST);
-    const long long nt = p.N / kTMr;
-    if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
+    const size_t smem = ring_smem<D, TMR>(p.K, NST);
+    const long long nt = p.N / TMR;
+    if (nt > 0x7fffffffLL || p.B > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
     int grid = sm_count();
     if (grid > nt) grid = (int)nt;
-    CUtensorMap gomap;
+    CUtensorMap gomap, zmap;
     memset(&gomap, 0, sizeof(gomap));
-    if (p.g_out != nullptr) {
-        if (p.B > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
-        const int rc = tc::make_plain_map(gomap, p.g_out, CTVQ_F32, p.HW, D, p.B, kTMr, D);
-        if (rc != CTVQ_OK) return rc;
-    }
-    CUtensorMap zmap;
-    if (p.B > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
-    if (tc::make_plain_map(zmap, p.z, CTVQ_F32, p.HW, D, p.B, kTMr, D) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
-    auto kern = vq_bwd_c1_ring_kernel<D, NST>;
+    if (p.g_out != nullptr && tc::make_plain_map(gomap, p.g_out, CTVQ_F32, p.HW, D, p.B, TMR, D) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
+    if (tc::make_plain_map(zmap, p.z, CTVQ_F32, p.HW, D, p.B, TMR, D) != CTVQ_OK) return CTVQ_E_UNSUPPORTED;
+    auto kern = vq_bwd_c1_ring_kernel<D, TMR, NST>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const int seg = p.HW / kTMr;
+    const int seg = p.HW / TMR;
     int seg_shift = -1;
     if ((seg & (seg - 1)) == 0)
         for (seg_shift = 0; (1 << seg_shift) < seg; ++seg_shift) {}
     kern<<<grid, kRingThreads, smem, s>>>(p, (int)nt, seg_shift, gomap, zmap);
     return (int)cudaGetLastError();
 }
+
+template <int D, int TMR>
+int launch_ring_nst(const BwdParams& p, cudaStream_t s) {
+    const size_t cap = 227 * 1024 - 256;  // static shared memory of the tail + slack
+    if (p.HW % TMR != 0 || p.N < (long long)sm_count() * TMR * 4) return CTVQ_E_UNSUPPORTED;
+    if (ring_smem<D, TMR>(p.K, 3) <= cap) return launch_ring<D, TMR, 3>(p, s);
+    if (ring_smem<D, TMR>(p.K, 2) <= cap) return launch_ring<D, TMR, 2>(p, s);
+    return CTVQ_E_UNSUPPORTED;
+}
 }  // namespace
 
 // CTVQ_E_UNSUPPORTED: not a single full-width fp32 codebook of 32 / 64 channels, H*W not a multiple of 64, unaligned
 // tensors, an accumulator beyond shared memory, or a batch too small to amortise zeroing + flushing it per CTA.
 int launch_backward_ring(const BwdParams& p, cudaStream_t s) {
-    // d = 32 tiles (8 KB) are too small for the per-tile hand-overs: measured 0.188 vs 0.145 ms for vq_bwd_c1_kernel at K=256, 1 M rows
-    if (p.dtype != CTVQ_F32 || p.C != 1 || p.d != p.Dtot || p.d != 64 || p.HW % kTMr != 0) return CTVQ_E_UNSUPPORTED;
-    if (p.K < 128 || p.K > 1024 || (p.K * p.d) % 4 != 0) return CTVQ_E_UNSUPPORTED;  // few codes: the ownership kernels of ctvq_bwd_fast.cu / the tiled kernel
+    if (p.dtype != CTVQ_F32 || p.C != 1 || p.d != p.Dtot) return CTVQ_E_UNSUPPORTED;
+    // the 16-bit list entries hold the code next to 6 (7 at 128-row tiles) row bits
+    if (p.K < 128 || p.K > (p.d == 32 ? 512 : 1024) || (p.K * p.d) % 4 != 0) return CTVQ_E_UNSUPPORTED;  // few codes: the ownership kernels of ctvq_bwd_fast.cu / the tiled kernel
     if ((reinterpret_cast<uintptr_t>(p.z) & 15) || (reinterpret_cast<uintptr_t>(p.gz) & 15) ||
         (p.g_out && (reinterpret_cast<uintptr_t>(p.g_out) & 15)) || (reinterpret_cast<uintptr_t>(p.idx) & 7))
         return CTVQ_E_UNSUPPORTED;
     // every CTA zeroes and flushes a [K, d] accumulator: only worth it when the rows outweigh that
-    if (p.N < (long long)sm_count() * kTMr * 4 || p.N < (long long)sm_count() * p.K) return CTVQ_E_UNSUPPORTED;
-    const size_t cap = 227 * 1024;
-    if (p.d == 64) {
-        if (ring_smem<64>(p.K, 3) <= cap) return launch_ring<64, 3>(p, s);
-        if (ring_smem<64>(p.K, 2) <= cap) return launch_ring<64, 2>(p, s);
-    } else {
-        if (ring_smem<32>(p.K, 3) <= cap) return launch_ring<32, 3>(p, s);
-        if (ring_smem<32>(p.K, 2) <= cap) return launch_ring<32, 2>(p, s);
-    }
+    if (p.N < (long long)sm_count() * p.K) return CTVQ_E_UNSUPPORTED;
+    if (p.d == 64) return launch_ring_nst<64, 64>(p, s);
+    if (p.d == 128) return launch_ring_nst<128, 32>(p, s);
+    if (p.d == 32) return launch_ring_nst<32, 128>(p, s);
     return CTVQ_E_UNSUPPORTED;
 }
 

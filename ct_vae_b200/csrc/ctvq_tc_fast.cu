@@ -92,22 +92,15 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     const uint32_t bar_full0 = smem_u32(&bars[0]), bar_empty0 = smem_u32(&bars[NSTAGE]);
     const uint32_t bar_m = smem_u32(&bars[2 * NSTAGE]), bar_tfree = smem_u32(&bars[2 * NSTAGE + 2]);
 
-    // ---- prologue, ordered so that nothing waits behind the first slabs' HBM traffic: (1) every thread's codebook row
-    // is requested FIRST (the 148 CTAs' opening TMA loads put ~15 MB into the memory system's queues; loads issued
-    // behind them measured ~3 us), (2) the producer thread initialises the barriers itself and starts the ring without
-    // a CTA-wide barrier, (3) the zero-fill runs underneath both.
-    float4 v[D / 4];
-    const int ck = tid % NK, cc = tid / NK;  // code, codebook of this thread (tid < C*NK)
-    if (tid < C * NK) {
-        if (ck < K) {
-            const float4* row = reinterpret_cast<const float4*>(p.E[cc] + (size_t)ck * D);
-#pragma unroll
-            for (int m = 0; m < D / 4; ++m) v[m] = __ldg(row + m);  // all loads in flight at once
-        } else {
-#pragma unroll
-            for (int m = 0; m < D / 4; ++m) v[m] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        }
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full0 + 8 * i, 1); mbar_init(bar_empty0 + 8 * i, 4 * C + 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_m + 8 * i, 1); mbar_init(bar_tfree + 8 * i, 4 * C); }
+        fence_barrier_init();
     }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+    __syncthreads();  // barriers initialised before the first TMA may signal them
+    if (tid == 0) stamp(P, 1);
+
     const int niter = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const bool producer = (tid == 128 * NWG);
     auto issue_tma = [&](int it) {  // producer only: TMA-load the tile of iteration `it` into its ring slot
@@ -125,13 +118,22 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
             tma_load_3d(a_base + st * kStage + mb * kBlk, &maps.m[seg], bar_full0 + 8 * st, (int)(nb - bb * HWT), 0, (int)bb);
         }
     };
-    if (producer) {  // the first tiles stream in while the codebooks are staged
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full0 + 8 * i, 1); mbar_init(bar_empty0 + 8 * i, 4 * C + 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_m + 8 * i, 1); mbar_init(bar_tfree + 8 * i, 4 * C); }
-        fence_barrier_init();  // visible to the async proxy; every other thread meets them after the __syncthreads below
+    if (producer)  // the first tiles stream in while the codebooks are staged
         for (int it = 0; it < NSTAGE && it < niter; ++it) issue_tma(it);
+
+    // ---- codebooks (once per persistent CTA), one code per thread: the global loads fly while everybody zero-fills ----
+    float4 v[D / 4];
+    const int ck = tid % NK, cc = tid / NK;  // code, codebook of this thread (tid < C*NK)
+    if (tid < C * NK) {
+        if (ck < K) {
+            const float4* row = reinterpret_cast<const float4*>(p.E[cc] + (size_t)ck * D);
+#pragma unroll
+            for (int m = 0; m < D / 4; ++m) v[m] = __ldg(row + m);  // all loads in flight at once
+        } else {
+#pragma unroll
+            for (int m = 0; m < D / 4; ++m) v[m] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
     }
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
     // zero the merged B operand, the slab channels no TMA box ever writes (they meet zero B columns, but 0 * garbage
     // could be NaN) and build the ones block
     for (int i = tid; i < (int)(2 * kBblk / 16); i += kFT) reinterpret_cast<float4*>(b_s)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -143,8 +145,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     for (int i = tid; i < 1024; i += kFT)  // rows are constant, so the swizzle inside a 128-byte row is immaterial
         reinterpret_cast<float*>(ones_s)[i] = ((i >> 5) & 7) < 3 ? 1.0f : 0.0f;
     if (tid < C) reinterpret_cast<unsigned*>(emax_s)[tid] = 0u;
-    __syncthreads();  // barriers, TMEM column base and the zero-fill are visible
-    if (tid == 0) stamp(P, 1);
+    __syncthreads();
     if (tid < C * NK) {
         // plain per-codebook copy (the epilogue gathers from it), merged B at the shifted K-columns, exact |e|^2
         float a = 0.0f;  // exact sequential chain (arithmetic contract)
@@ -182,7 +183,9 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (tid < C) emax_s[tid] = sqrtf(__uint_as_float(reinterpret_cast<unsigned*>(emax_s)[tid])) * 1.0001f;
     const uint32_t tmem_base = *tmem_slot;
+    __syncthreads();
     if (tid == 0) stamp(P, 2);
 
     float lsum[C];
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
             for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ (x + c * CS)) & 3) << 5) + ((lane & 7) << 2);
             const float* ee = ee_s + c * NK;
             const uint8_t* ecb = e_s + (size_t)c * kEcb;
-            const float emax = sqrtf(emax_s[c]) * 1.0001f;  // emax_s holds max |e|^2 (its bits were the atomicMax key)
+            const float emax = emax_s[c];
             const int tile = blockIdx.x + it * gridDim.x;
             const int seg = tile / p.tiles_per_seg;
             const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;

@@ -173,7 +173,8 @@ def test_pair_batching_matches_two_calls(env):
     ("fast_c2_hw256_big_tma_backward", 160, 64, 16, 16, 2, 64, "init"),
     ("sweep_d32_k256", 256, 32, 16, 16, 1, 256, "trained"),
     ("ring_bwd_cfg1_k512_d64", 320, 64, 16, 16, 1, 512, "init"),        # resident-accumulator ring backward (ctvq_bwd_ring.cu), config-1 codebook
-    ("ring_bwd_k256_d32", 160, 32, 16, 16, 1, 256, "trained"),          # ... one channel chunk, four code residue classes
+    ("ring_bwd_k256_d32", 320, 32, 16, 16, 1, 256, "trained"),          # ... one channel chunk, eight code residue classes, 128-row tiles
+    ("ring_bwd_k256_d128", 160, 128, 16, 16, 1, 256, "trained"),        # ... four channel chunks, 32-row tiles
     ("ring_bwd_k130_d64_hw64", 640, 64, 8, 8, 1, 130, "trained"),       # ... one tile per image, ragged K
     ("sweep_d128_k1024", 64, 128, 16, 16, 1, 1024, "trained"),
     ("sweep_d256_k256", 16, 256, 16, 16, 1, 256, "init"),
