@@ -667,35 +667,64 @@ def main():
             raise RuntimeError(f"collective check failed: {collective_check}")
 
     # ---- e2e: public API; latents from pinned host memory each step; output, indices and loss copied back -------------
-    e2e_steps = max(3, min(args.steps, 10))
-    host_z = torch.randn(B, D, H, W).pin_memory()
-    host_q = torch.empty(B, D, H, W).pin_memory()
-    host_i = torch.empty(B, C, H, W, dtype=torch.int64).pin_memory()
-    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
-    dz = torch.empty(B, D, H, W, device=dev, requires_grad=True)
+    # Double-buffered like a prefetching data loader: the H2D copy of step i+1 and the D2H copies of step i-1 run on their
+    # own streams (PCIe is full duplex) while step i computes; every step's copies are inside the timed region, and the
+    # host reads each step's loss (experiment.py:96 .item()) as soon as that step's read-back has landed.
+    e2e_steps = max(4, min(args.steps, 30))
+    NB = 2
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    host_z = [torch.randn(B, D, H, W).pin_memory() for _ in range(NB)]
+    host_q = [torch.empty(B, D, H, W).pin_memory() for _ in range(NB)]
+    host_i = [torch.empty(B, C, H, W, dtype=torch.int64).pin_memory() for _ in range(NB)]
+    host_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(NB)]
+    dzs = [torch.empty(B, D, H, W, device=dev, requires_grad=True) for _ in range(NB)]
+    ev_in = [torch.cuda.Event() for _ in range(NB)]
+    ev_c = [torch.cuda.Event() for _ in range(NB)]
+    ev_out = [torch.cuda.Event() for _ in range(NB)]
+    keep = [None] * NB  # a step's device outputs stay referenced until its read-back has been consumed
 
-    def e2e_step():
-        with torch.no_grad():
-            dz.copy_(host_z, non_blocking=True)
-        out, loss, inds = m(dz, inds=True)
+    def e2e_issue(i):
+        b = i % NB
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_c[b])  # the step that last read this device buffer has finished
+            with torch.no_grad():
+                dzs[b].copy_(host_z[b], non_blocking=True)
+            ev_in[b].record(s_in)
+        cur.wait_event(ev_in[b])
+        out, loss, inds = m(dzs[b], inds=True)
         torch.autograd.backward([out, loss], [g_out, g_loss])
-        host_q.copy_(out.detach(), non_blocking=True)
-        host_i.copy_(inds, non_blocking=True)
-        host_loss.copy_(loss.detach(), non_blocking=True)
-        dz.grad = None
+        ev_c[b].record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_c[b])
+            host_q[b].copy_(out.detach(), non_blocking=True)
+            host_i[b].copy_(inds, non_blocking=True)
+            host_loss[b].copy_(loss.detach(), non_blocking=True)
+            ev_out[b].record(s_out)
+        keep[b] = (out, inds, loss)
+        dzs[b].grad = None
         for p in params:
             p.grad = None
-        torch.cuda.current_stream().synchronize()  # the user reads the loss (experiment.py:96 .item())
-        return float(host_loss)
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_collect(i):
+        ev_out[i % NB].synchronize()
+        return float(host_loss[i % NB])
+
+    def e2e_run(n):
+        for i in range(n):
+            e2e_issue(i)
+            if i >= 1:
+                e2e_collect(i - 1)
+        e2e_collect(n - 1)
+        cur.wait_stream(s_out)
+
+    e2e_run(3)
     sync_all()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    s_in.wait_stream(cur)
+    e2e_run(e2e_steps)
     t1.record()
     sync_all()
     te = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
@@ -704,7 +733,7 @@ def main():
     e2e_val = rows_per_gpu * world * e2e_steps / (float(te) * 1e-3)
     h2d = B * D * H * W * 4
     d2h = B * D * H * W * 4 + B * C * H * W * 8 + 4
-    del host_z, host_q, host_i, dz
+    del host_z, host_q, host_i, dzs, keep
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------
     hbm_peak, tc_peak, peak_src = peaks()
@@ -717,11 +746,11 @@ def main():
     ]
     # DRAM traffic per launch: NOT measured by this run (it needs ncu); the figures come from the committed
     # `ncu --set full` capture of this very workload and are quoted only for the profiled batch size
-    ncu_traffic = {16384: (146883328 + 511268352, 717339648 + 497255936)}.get(B)
+    ncu_traffic = {16384: (146948864 + 511877376, 717344000 + 497388032)}.get(B)
     for i, k in enumerate(kernels):
         k["frac"] = k["gbs"] / hbm_peak
         k["traffic"] = ncu_traffic[i] if ncu_traffic else None
-        k["traffic_source"] = "ncu capture profiles/r1_fwd_ws_b16384.md (dram__bytes_read.sum + dram__bytes_write.sum)" if ncu_traffic else None
+        k["traffic_source"] = "ncu capture profiles/r2_cfg2_fp32.md (dram__bytes_read.sum + dram__bytes_write.sum)" if ncu_traffic else None
     dom = max(kernels, key=lambda k: k["ms"])
     roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"],
                 "traffic": dom["traffic"], "traffic_source": dom["traffic_source"], "kernel": dom["kernel"],
@@ -758,7 +787,8 @@ def main():
                                       + ("; device-side rendezvous (all-reduce) before the first event" if world > 1 else "")),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
-                        "what": "latents H2D from pinned memory; quantised output, int64 indices and loss D2H; forward + backward"},
+                        "what": "every step: latents H2D from pinned memory, forward + backward, quantised output + int64 indices + loss D2H, loss "
+                                "read by the host; double-buffered (copies of neighbouring steps overlap the compute on separate streams)"},
                 "gpu_launches": (2 + (1 if world > 1 and not fused else 0)) * args.steps,
                 "collective_check": collective_check, "roofline": roofline, "kernels": kernels, "clocks": clocks,
                 "parity": parity, "sub_records": subs, "latency_at_config_batch": lat,
