@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_bf16_kernel(const
             for (int it = 0; it < niter; ++it) {
                 const int st = it % NSTAGE, buf = it & 1;
                 const uint32_t stage_u32 = a_base + st * kStage;
-                mbar_wait_fast(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
-                if (it >= 2) mbar_wait_fast(bar_tfree + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u);
+                mbar_wait_sleep(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
+                if (it >= 2) mbar_wait_sleep(bar_tfree + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u);
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + buf * 256;
 #pragma unroll
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_bf16_kernel(const
                 umma_commit(bar_empty0 + 8 * st);
                 while (tma_next < niter && tma_next <= it + NSTAGE - 1) {
                     const int prev = tma_next - NSTAGE;
-                    mbar_wait_fast(bar_empty0 + 8 * (prev % NSTAGE), (uint32_t)(prev / NSTAGE) & 1u);
+                    mbar_wait_sleep(bar_empty0 + 8 * (prev % NSTAGE), (uint32_t)(prev / NSTAGE) & 1u);
                     issue_tma(tma_next);
                     ++tma_next;
                 }

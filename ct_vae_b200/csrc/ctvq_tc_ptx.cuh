@@ -56,6 +56,30 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// Producer-lane wait: the same bounded wait with a nanosleep back-off between polls.  A single-lane producer spends most of
+// its life waiting (it runs two tiles ahead), and its polling loop competes for issue slots with the four epilogue warps of
+// its scheduler: round-2 ncu of the config-2 forward showed 13 % of all executed instructions in these loops and the
+// producer's scheduler executing 15 % more instructions than the other three.  A ~0.1 us reaction time is irrelevant two
+// tiles ahead.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    long long t0 = 0;
+#pragma unroll 1
+    for (unsigned it = 0;; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+        if (ok) return;
+        __nanosleep(100);
+        if ((it & 1023u) == 1023u) {
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 8000000000LL) __trap();
+        }
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
             for (int nx = NSTAGE; nx < niter; ++nx) {
                 const int prev = nx - NSTAGE;
                 if (nx + kL2Ahead < niter) issue_tma(nx + kL2Ahead, true);
-                mbar_wait_fast(bar_empty0 + 8 * (prev % NSTAGE), (uint32_t)(prev / NSTAGE) & 1u);
+                mbar_wait_sleep(bar_empty0 + 8 * (prev % NSTAGE), (uint32_t)(prev / NSTAGE) & 1u);
                 issue_tma(nx, false);
             }
         }
@@ -223,15 +223,15 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
         if (lane == 0) {
             const uint32_t idesc = instr_desc_tf32(NKU);
             const uint32_t idesc_x = idesc | (1u << 16);  // extra K-group: B operand MN-major as well
-            mbar_wait_fast(bar_bfull, 0u);
+            mbar_wait_sleep(bar_bfull, 0u);
             for (int it = 0; it < niter; ++it) {
                 const int st = it % NSTAGE;
                 const uint32_t stage_u32 = a_base + st * kStage;
-                mbar_wait_fast(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
+                mbar_wait_sleep(bar_full0 + 8 * st, (uint32_t)(it / NSTAGE) & 1u);
 #pragma unroll 1
                 for (int h = 0; h < NH; ++h) {
                     const int u = it * NH + h, buf = u & 1;
-                    if (u >= 2) mbar_wait_fast(bar_tfree + 8 * buf, (uint32_t)((u >> 1) - 1) & 1u);
+                    if (u >= 2) mbar_wait_sleep(bar_tfree + 8 * buf, (uint32_t)((u >> 1) - 1) & 1u);
                     tc_fence_after();
                     const uint32_t dcol = tmem_base + buf * NKU;
 #pragma unroll

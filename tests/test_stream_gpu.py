@@ -101,15 +101,14 @@ def test_stream_pair_batching(env):
     assert torch.equal(iy.cpu().reshape(16, 1, 8, 8), CO.argmin(y.cpu(), book))
 
 
-@pytest.mark.parametrize("path", ["simt", "tc", "stream"])
-@pytest.mark.parametrize("shape", [(64, 1, 512), (128, 4, 64), (32, 1, 256)])
+# (the streaming kernel is single-codebook: that combination is not generated)
+@pytest.mark.parametrize("path,shape", [(p, s) for s in [(64, 1, 512), (128, 4, 64), (32, 1, 256)]
+                                        for p in ["simt", "tc", "stream"] if not (p == "stream" and s[1] != 1)])
 def test_non_finite_rows_follow_torch_argmin(env, path, shape):
     """NaN / inf latents: torch.argmin returns the first NaN distance (verified against the live reference when the
     goldens were minted); every kernel path and the C oracle must agree with torch on those rows."""
     pkg, _lib, O, CO = env
     D, C, K = shape
-    if path == "stream" and C != 1:
-        pytest.skip("streaming kernel is single-codebook")
     dev = torch.device("cuda:0")
     torch.manual_seed(11)
     d = D // C
@@ -128,12 +127,7 @@ def test_non_finite_rows_follow_torch_argmin(env, path, shape):
     z_cpu[2, d - 1, 7, 7] = float("-inf")
     z_cpu[3, 5, 4, 4] = 3.0e38   # |z|^2 overflows to +inf
     _lib.set_path({"simt": _lib.PATH_SIMT, "tc": _lib.PATH_TC, "stream": _lib.PATH_TC_STREAM}[path])
-    try:
-        inds = m.compute_inds(z_cpu.to(dev))
-    except RuntimeError as e:
-        if "unsupported" in str(e):
-            pytest.skip("shape not covered by this path")
-        raise
+    inds = m.compute_inds(z_cpu.to(dev))  # every generated (path, shape) pair is inside that path's domain
     books_cpu = [e.detach().cpu() for e in books]
     ref = O.mcq_compute_inds(z_cpu, books_cpu)   # the reference's ATen arithmetic, torch.argmin semantics
     got = inds.cpu().reshape(ref.shape)
