@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                 const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + team * TCOLS + slot * 64;
                 unsigned mask0 = 0u, mask1 = 0u;
                 float mxu = 0.0f;
+                bool hit = false;  // some score of this unit lies inside this row's window
                 if (valid) {
                     uint32_t a[32];
                     float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
@@ -331,6 +332,14 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                     }
                     mxu = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                     run_mx = fmaxf(run_mx, mxu);
+                    hit = mxu >= run_mx - 0.5f * thr;
+                }
+                // pass 2 only when SOME row of this warp has a score of this unit inside its window (a unit whose maximum is
+                // below the row's limit has no survivor): with K in the thousands the running maximum settles early and most
+                // later units are skipped -- a warp of 32 rows runs pass 2 on ~ 32 (1 + ln(units / 32)) units (98 of 256 at
+                // K = 16384).  The vote is taken by the whole (converged) warp.
+                if (__any_sync(0xffffffffu, hit)) {
+                    uint32_t a[32];
                     const float lim = run_mx - 0.5f * thr;  // running maximum: a superset of the final survivor set
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -342,6 +351,7 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                         const unsigned m = (mk[0] | mk[1]) | (mk[2] | mk[3]);
                         if (h == 0) mask0 = m; else mask1 = m;
                     }
+                    if (!valid) { mask0 = 0u; mask1 = 0u; }
                 }
                 tc_fence_before();
                 __syncwarp();
