@@ -35,6 +35,11 @@ SHAPES = [
     (5, 128, 8, 8, 1, 128, 64, 1, "auto"),    # config 3
     (600, 128, 8, 8, 1, 128, 64, 1, "auto"),  # config 3, large enough for the C=1 TMA-ring backward (N >= 18944)
     (7, 64, 16, 16, 1, 64, 300, 1, "auto"),   # resident-codebook forward, two units, partial last tile
+    (300, 64, 16, 16, 1, 64, 512, 1, "auto"), # config 1, large enough for the resident-accumulator ring backward (N >= 75776)
+    (160, 128, 16, 16, 1, 128, 256, 1, "auto"),  # ring backward, 32-row tiles (d = 128)
+    (320, 32, 16, 16, 1, 32, 256, 1, "auto"), # ring backward, 128-row tiles (d = 32)
+    (150, 128, 16, 16, 4, 32, 64, 1, "auto"), # config 2 on 128x128 images: TMA-ring backward on 64-position segments
+    (600, 64, 8, 8, 2, 32, 64, 1, "auto"),    # two codebooks: TMA-ring backward
     (3, 48, 8, 4, 2, 24, 50, 24, "auto"),     # generic tcgen05 kernel (K padded to 64, HW = 32)
     (2, 15, 3, 3, 5, 3, 7, 1, "auto"),        # ragged: SIMT + direct-atomic backward
     (6, 128, 8, 8, 4, 32, 64, 1, "simt"),

@@ -1,7 +1,7 @@
 """Tests of the NVLink peer-memory all-reduce (ctvq_peer_*, ctvq_backward_allreduce; protocol in csrc/ctvq_peer.cuh).
 
   * ONE GPU, world = 1 (never skipped): the fused tail runs in the last CTA of EVERY backward kernel family (TMA-ring,
-    shape-specialised, single-codebook shared-atomic, tiled, direct-atomic) and must reproduce the plain backward's
+    shape-specialised, single-codebook shared-atomic and ring, tiled, direct-atomic) and must reproduce the plain backward's
     codebook gradient bit for bit, over many epochs (slot parity), with grad_z untouched.
   * TWO GPUs (skipped below 2): the reduced gradient equals the rank-ordered sum / world of the per-rank gradients,
     bit-identically on both ranks, stand-alone and end to end through the module's backward."""
@@ -110,6 +110,9 @@ def one_rank_group():
     ("cfg2_small", 8, 128, 8, 8, 4, 64),
     ("cfg3", 32, 128, 8, 8, 1, 64),
     ("cfg1_shared_atomic", 256, 64, 16, 16, 1, 512),
+    ("cfg1_ring", 320, 64, 16, 16, 1, 512),                  # resident-accumulator ring kernel (ctvq_bwd_ring.cu)
+    ("ring_d128_rows32", 160, 128, 16, 16, 1, 256),          # ... 32-row tiles
+    ("cfg2_hw256_segments", 160, 128, 16, 16, 4, 64),        # TMA-ring kernel on 64-position segments (tensor-map g_out ring)
     ("tiled_c2", 64, 48, 8, 8, 2, 50),
     ("direct_atomic_ragged", 3, 15, 3, 3, 5, 7),
 ])
