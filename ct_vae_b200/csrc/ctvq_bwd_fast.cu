@@ -502,8 +502,9 @@ int launch_tma(const BwdParams& p, cudaStream_t s) {
 //     sm_100a) leave q - z IN PLACE of z, so the NGZ "gz" warps compute grad_z = g_out - coef_z (q - z) from shared memory only
 //     -- no index decode, no codebook copy padded for row-wise gathers.
 template <int D, int K, int HWT, int NST>
-__global__ void __launch_bounds__(256, 1) vq_bwd_c1_tma_kernel(const BwdParams p, const int ntiles) {
-    constexpr int TM = HWT;
+__global__ void __launch_bounds__(256, 1) vq_bwd_c1_tma_kernel(const BwdParams p, const int ntiles, const __grid_constant__ CUtensorMap gomap) {
+    constexpr int TM = 64;                 // rows per tile: one 64-position segment of an image (the whole image at H*W = 64)
+    constexpr int SEG = HWT / TM;          // tiles per image
     constexpr int ZS = TM + 1;
     constexpr int KD = K * D;
     constexpr int JCH = D / 32;            // acc warps
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(256, 1) vq_bwd_c1_tma_kernel(const BwdParams p
     constexpr int NAT = JCH * 32, NGT = NGZ * 32;
     constexpr int GOF = D * TM;            // floats per g_out stage
     constexpr int kDiff = 1, kAcc = 3, kGz = 4;  // named barrier ids (kDiff + buf)
-    static_assert(D % 32 == 0 && JCH >= 1 && JCH <= 4 && TM == 64 && (D * TM) % NGT == 0, "shape");
+    static_assert(D % 32 == 0 && JCH >= 1 && JCH <= 4 && HWT % TM == 0 && (D * TM) % NGT == 0, "shape");
     extern __shared__ __align__(128) float smem[];
     float* go_s = smem;                                        // [NST][D][TM]
     int* idx_s = reinterpret_cast<int*>(go_s + NST * GOF);     // [2][TM]
@@ -537,12 +538,14 @@ __global__ void __launch_bounds__(256, 1) vq_bwd_c1_tma_kernel(const BwdParams p
 
     if (warp < JCH) {
         // =========================== acc warps: codebook-gradient accumulation, q - z left in place ===========================
-        auto issue_go = [&](int it) {  // thread 0: stream image it's g_out block into ring slot it % NST
+        auto issue_go = [&](int it) {  // thread 0: stream tile it's g_out block into ring slot it % NST
             const int st = it % NST;
             if (it >= NST) mbar_wait(bar_empty + 8 * st, (uint32_t)((it / NST) - 1) & 1u);
-            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long t = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long b = t / SEG;
             mbar_expect_tx(bar_full + 8 * st, GOF * 4u);
-            bulk_g2s(smem_u32(go_s + st * GOF), p.g_out + (size_t)b * GOF, GOF * 4u, bar_full + 8 * st);
+            if (SEG == 1) bulk_g2s(smem_u32(go_s + st * GOF), p.g_out + (size_t)b * GOF, GOF * 4u, bar_full + 8 * st);
+            else tc::tma_load_3d(smem_u32(go_s + st * GOF), &gomap, bar_full + 8 * st, (int)(t - b * SEG) * TM, 0, (int)b);  // box [D][64]
         };
         if (tid == 0 && has_go)
             for (int it = 0; it < NST - 1 && it < niter; ++it) issue_go(it);
@@ -550,8 +553,9 @@ __global__ void __launch_bounds__(256, 1) vq_bwd_c1_tma_kernel(const BwdParams p
             const int buf = it & 1;
             if (tid == 0 && has_go && it + NST - 1 < niter) issue_go(it + NST - 1);
             if (tid < TM) {  // this tile's indices (range-checked like every consumer of caller-supplied indices)
-                const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
-                long long kk = __ldg(p.idx + (size_t)b * HWT + tid);
+                const long long t = (long long)blockIdx.x + (long long)it * gridDim.x;
+                const long long b = t / SEG;
+                long long kk = __ldg(p.idx + (size_t)b * HWT + (int)(t - b * SEG) * TM + tid);
                 if (kk < 0 || kk >= K) { atomicOr(p.err, 1u); kk = kk < 0 ? 0 : K - 1; }
                 idx_s[buf * TM + tid] = (int)kk;
             }
@@ -597,24 +601,27 @@ __global__ void __launch_bounds__(256, 1) vq_bwd_c1_tma_kernel(const BwdParams p
         const int m = (lane & 15) * 4;           // rows m..m+3
         constexpr int CPT = D * TM / NGT;        // 4-byte copies per thread per tile
         auto stage = [&](int it) {               // tile it -> buffer it & 1 (asynchronous; completion arrives on zfull[buf])
-            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long t = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long b = t / SEG;
             const int buf = it & 1;
-            const float* src = p.z + (size_t)b * D * HWT;
+            const float* src = p.z + (size_t)b * D * HWT + (int)(t - b * SEG) * TM;
             float* dst = zs + buf * D * ZS;
 #pragma unroll 8
             for (int i = 0; i < CPT; ++i) {
-                const int e = i * NGT + gt;      // element of the [D][TM] image block: coalesced along H*W
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + (e / TM) * ZS + (e % TM))), "l"(src + e) : "memory");
+                const int e = i * NGT + gt;      // element of the [D][TM] block: coalesced along H*W
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + (e / TM) * ZS + (e % TM))),
+                             "l"(src + (size_t)(e / TM) * HWT + (e % TM)) : "memory");
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_zfull + 8 * buf) : "memory");
         };
         for (int it = 0; it < 2 && it < niter; ++it) stage(it);
         for (int it = 0; it < niter; ++it) {
             const int buf = it & 1, st = it % NST;
-            const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long t = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long b = t / SEG;
             const float* zb = zs + buf * D * ZS;
             const float* gos = go_s + st * GOF;
-            float* gz_row = p.gz + (size_t)b * D * HWT + m;
+            float* gz_row = p.gz + (size_t)b * D * HWT + (int)(t - b * SEG) * TM + m;
             named_sync(kDiff + buf, 256);
             if (has_go) mbar_wait(bar_full + 8 * st, (uint32_t)(it / NST) & 1u);
 #pragma unroll 4
@@ -643,17 +650,25 @@ __global__ void __launch_bounds__(256, 1) vq_bwd_c1_tma_kernel(const BwdParams p
 
 template <int D, int K, int HWT, int NST>
 int launch_c1_tma(const BwdParams& p, cudaStream_t s) {
-    constexpr size_t smem = sizeof(float) * ((size_t)NST * D * HWT + 2 * (size_t)HWT + 2 * (size_t)D * (HWT + 1) + 2 * (size_t)K * D) + (2 * NST + 2) * 8;
+    constexpr int TM = 64;
+    constexpr size_t smem = sizeof(float) * ((size_t)NST * D * TM + 2 * (size_t)TM + 2 * (size_t)D * (TM + 1) + 2 * (size_t)K * D) + (2 * NST + 2) * 8;
     static_assert(smem <= 227 * 1024, "shared memory");
     if (p.N % HWT != 0) return CTVQ_E_UNSUPPORTED;
-    const long long nt = p.N / HWT;  // one image per tile
+    const long long nt = p.N / TM;  // one 64-position segment of an image per tile
     if (nt > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
     int grid = sm_count();
     if (grid > nt) grid = (int)nt;
+    CUtensorMap gomap;
+    memset(&gomap, 0, sizeof(gomap));
+    if (HWT != TM && p.g_out != nullptr) {
+        if (p.B > 0x7fffffffLL) return CTVQ_E_UNSUPPORTED;
+        const int rc = tc::make_plain_map(gomap, p.g_out, CTVQ_F32, HWT, D, p.B, TM, D);
+        if (rc != CTVQ_OK) return rc;
+    }
     auto kern = vq_bwd_c1_tma_kernel<D, K, HWT, NST>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, 256, smem, s>>>(p, (int)nt);
+    kern<<<grid, 256, smem, s>>>(p, (int)nt, gomap);
     return (int)cudaGetLastError();
 }
 }  // namespace
@@ -693,6 +708,10 @@ int launch_backward_fast(const BwdParams& p, cudaStream_t s) {
         if (ok && p.N >= (long long)sm_count() * 64 * 2 && !no_tma) return launch_c1_tma<128, 64, 64, 2>(p, s);
         return launch<128, 1, 64, 64, 128, 1, 1>(p, s);
     }
+    // the same model on 128x128 images (H*W = 256): 64-position segments, g_out by one tensor-map box per tile
+    if (p.d == 128 && p.C == 1 && p.K == 64 && p.HW == 256 && p.Dtot == 128 && (reinterpret_cast<uintptr_t>(p.z) & 3) == 0 &&
+        (p.g_out == nullptr || (reinterpret_cast<uintptr_t>(p.g_out) & 127) == 0) && p.N >= (long long)sm_count() * 64 * 2 && !no_tma)
+        return launch_c1_tma<128, 64, 256, 2>(p, s);
     return CTVQ_E_UNSUPPORTED;
 }
 

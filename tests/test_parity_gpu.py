@@ -173,6 +173,7 @@ def test_pair_batching_matches_two_calls(env):
     ("cfg3_trained", 32, 128, 8, 8, 1, 64, "trained"),    # configs/ct_mcq_vae.yaml (x and y)
     ("cfg3_big_tma_backward", 512, 128, 8, 8, 1, 64, "trained"),   # large enough for the C=1 TMA-ring backward kernel
     ("cfg3_init_ties", 40, 128, 8, 8, 1, 64, "init"),
+    ("cfg3_hw256_big_tma_backward", 80, 128, 16, 16, 1, 64, "trained"),  # config 3 on 128x128 images: 64-position segments
     ("res_d64_k300", 24, 64, 16, 16, 1, 300, "trained"),  # resident-codebook kernel, ragged second unit
     ("res_d32_k700", 12, 32, 16, 16, 1, 700, "init"),     # ... three units padded to four
     ("res_d64_k64", 24, 64, 8, 8, 1, 64, "trained"),      # ... 64-column units

@@ -20,6 +20,7 @@ PTS = {
     "k1024d64": (1 << 20, 64, 1024, 1, 256, "trained"),
     "c4hw256": (1 << 20, 128, 64, 4, 256, "trained"),
     "c2hw64": (1 << 20, 64, 64, 2, 64, "trained"),
+    "cfg3hw256": (1 << 20, 128, 64, 1, 256, "trained"),
     "k4096d128": (1 << 18, 128, 4096, 1, 256, "trained"),
     "k16384d32": (1 << 20, 32, 16384, 1, 256, "trained"),
     "k16384d256": (1 << 16, 256, 16384, 1, 256, "trained"),
