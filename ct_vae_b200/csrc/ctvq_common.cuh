@@ -76,6 +76,17 @@ template <> struct IO<__nv_bfloat16> {
 // the near-tie count falls out of the exact re-scoring loop.
 constexpr float kWinAbs = 9.5367431640625e-7f + 1.0e-6f;
 
+// tcgen05.mma kind::tf32 TRUNCATES its fp32 operands to 10 explicit mantissa bits (measured: tools/tf32_rounding_probe.py,
+// pinned by tests/test_stream_gpu.py::test_tf32_operands_are_truncated): x_hi = x (1 - dx), dx in [0, 2^-10), so every
+// product is z e (1 - dz)(1 - de) with (1 - dz)(1 - de) in (c - 2^-10, c + 2^-10], c = 1 - 2^-10.  Dividing the tensor-core
+// dot product by c CENTRES the error:  |dot_tf32 / c - z.e| <= (2^-10 / c) sum |z_j e_j| <= kTf32Eps |z||e|  -- half the
+// uncentred bound 2^-9 |z||e|, for free: the kernels whose accumulator holds  z.e - |e|^2/2  scale the exact |e|^2 term by
+// c instead (the score is then c times the true one, which only makes the window a hair wider), the others fold 1/c into
+// the -2 they multiply the dot product with.  Half the window is roughly half the rows that need exact re-scoring.
+constexpr float kTruncC = 1.0f - 9.765625e-4f;    // 1 - 2^-10, exact in fp32
+constexpr float kTf32Eps = 1.03e-3f;              // >= 2^-10 / c = 9.775e-4 (5 % slack, as the uncentred 2.05e-3 had over 2^-9)
+constexpr float kNeg2OverC = -2.0f / kTruncC;     // -2.00195...: dot product -> distance units, centred
+
 // near-tie predicate on the exact fp32 distances d1 <= d2 of the best and second-best code (d2 = +inf: single code)
 __device__ __forceinline__ bool near_tie(float d1, float d2) {
     return __fsub_rn(d2, d1) <= __fmul_rn(CTVQ_NEAR_TIE_REL, fabsf(d1));  // '<=': an exact tie at distance 0 counts too

@@ -176,13 +176,13 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int kk = blk * 32 + i;
-                        if (kk < w) mn = fminf(mn, fmaf(-2.0f, v[i], ee[kk]));
+                        if (kk < w) mn = fminf(mn, fmaf(kNeg2OverC, v[i], ee[kk]));
                         if (P.dbg && kk < w) P.dbg[((size_t)tile * kTM + tid) * (C * Kpad) + c * Kpad + kk] = v[i];
                     }
                 }
                 // rigorous bound on |tf32 distance - exact-chain distance|: operands truncated to 11 bits
                 const float emax = emax_s[c];
-                const float thr = 2.0f * (0.00390625f * sqrtf(zz) * 1.0001f * emax + kWinAbs * (zz + emax * emax));
+                const float thr = 2.0f * (2.0f * kTf32Eps * sqrtf(zz) * 1.0001f * emax + kWinAbs * (zz + emax * emax));
                 if (ch == 0) { run_mn = CUDART_INF_F; run_bv = CUDART_INF_F; run_bv2 = CUDART_INF_F; run_bi = 0x7fffffff; run_bad = false; }
                 run_mn = fminf(run_mn, mn);
                 const float lim = run_mn + thr;  // running minimum: a superset of the final survivor set
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kThreads) vq_fwd_tc_kernel(const TcParams P, c
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int kk = blk * 32 + i;
-                            if (kk < w && fmaf(-2.0f, v[i], ee[kk]) <= lim) mask[blk] |= 1u << i;
+                            if (kk < w && fmaf(kNeg2OverC, v[i], ee[kk]) <= lim) mask[blk] |= 1u << i;
                         }
                         cnt += __popc(mask[blk]);
                     }

@@ -196,14 +196,14 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
 #pragma unroll
                     for (int i = 0; i < 64; i += 4) {
                         const float4 e4 = *reinterpret_cast<const float4*>(ee + chn * 64 + i);
-                        a[i] = fmaf(-2.0f, a[i], e4.x); a[i + 1] = fmaf(-2.0f, a[i + 1], e4.y);
-                        a[i + 2] = fmaf(-2.0f, a[i + 2], e4.z); a[i + 3] = fmaf(-2.0f, a[i + 3], e4.w);
+                        a[i] = fmaf(kNeg2OverC, a[i], e4.x); a[i + 1] = fmaf(kNeg2OverC, a[i + 1], e4.y);
+                        a[i + 2] = fmaf(kNeg2OverC, a[i + 2], e4.z); a[i + 3] = fmaf(kNeg2OverC, a[i + 3], e4.w);
                         m0 = fminf(m0, a[i]); m1 = fminf(m1, a[i + 1]); m2 = fminf(m2, a[i + 2]); m3 = fminf(m3, a[i + 3]);
                     }
                 }
                 const float mn = fminf(fminf(m0, m1), fminf(m2, m3));
                 run_mn = fminf(run_mn, mn);
-                const float thr = 2.0f * (2.0f * 2.05e-3f * sqrtf(zz) * 1.0001f * emax + kWinAbs * (zz + emax * emax));
+                const float thr = 2.0f * (2.0f * kTf32Eps * sqrtf(zz) * 1.0001f * emax + kWinAbs * (zz + emax * emax));
                 const float lim = run_mn + thr;  // running minimum: a superset of the final survivor set
                 unsigned mask[NCH * 2];
                 int cnt = 0;
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(kCT, MINB) vq_fwd_tc_c1_kernel(const C1Params 
 #pragma unroll
                         for (int i = 0; i < 64; i += 4) {
                             const float4 e4 = *reinterpret_cast<const float4*>(ee + chn * 64 + i);
-                            a[i] = fmaf(-2.0f, a[i], e4.x); a[i + 1] = fmaf(-2.0f, a[i + 1], e4.y);
-                            a[i + 2] = fmaf(-2.0f, a[i + 2], e4.z); a[i + 3] = fmaf(-2.0f, a[i + 3], e4.w);
+                            a[i] = fmaf(kNeg2OverC, a[i], e4.x); a[i + 1] = fmaf(kNeg2OverC, a[i + 1], e4.y);
+                            a[i + 2] = fmaf(kNeg2OverC, a[i + 2], e4.z); a[i + 3] = fmaf(kNeg2OverC, a[i + 3], e4.w);
                         }
                     }
                     unsigned lo = 0u, hi = 0u;

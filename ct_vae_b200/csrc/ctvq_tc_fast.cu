@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
         // hugely negative score so they never survive the filter
         float t0 = -1.0e30f, t1 = 0.0f, t2 = 0.0f;
         if (a < CUDART_INF_F) {
-            const float h = -0.5f * a;
+            const float h = (-0.5f * kTruncC) * a;  // centred truncation error (ctvq_common.cuh)
             t0 = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
             const float r1 = h - t0;
             t1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
                 // rigorous bound on |tf32 distance - exact-chain distance|: both operands lose at most
                 // 2^-10 relative (truncation to 10 mantissa bits) -> |dot error| <= (2^-9 + slack) |z||e|; scores are
                 // distances / -2, so the window is half the distance bound
-                const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx(zzc) * 1.0001f * emax + kWinAbs * (zzc + emax * emax));
+                const float thr = 2.0f * (2.0f * kTf32Eps * sqrt_approx(zzc) * 1.0001f * emax + kWinAbs * (zzc + emax * emax));
                 const float lim = mx - 0.5f * thr;
                 // ---- pass 2: survivors as a bitmask (four independent accumulators per half); the upper half is still in
                 // registers from pass 1, only the lower half is re-read from TMEM

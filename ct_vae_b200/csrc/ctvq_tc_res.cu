@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
         const float a = __ldg(P.ee + n);
         float t[8] = {-1.0e30f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // padded / overflowed codes never survive the filter
         if (a < CUDART_INF_F) {
-            const float h = -0.5f * a;
+            const float h = (-0.5f * kTruncC) * a;  // centred truncation error (ctvq_common.cuh)
             t[0] = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
             const float r1 = h - t[0];
             t[1] = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
                     if (h == 0) {
                         zzu = ((pz_s[r] + pz_s[128 + r]) + (pz_s[256 + r] + pz_s[384 + r])) * 1.00001f;  // >= the exact chain value
                         // rigorous bound on |tf32 distance - exact-chain distance|; scores are distances / -2
-                        thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx_r(zzu) * 1.0001f * emax + kWinAbs * (zzu + emax * emax));
+                        thr = 2.0f * (2.0f * kTf32Eps * sqrt_approx_r(zzu) * 1.0001f * emax + kWinAbs * (zzu + emax * emax));
                     }
                     const float lim = run - 0.5f * thr;  // running maximum: a superset of the final survivor set
                     // ---- pass 2: survivors as a bitmask (both halves re-read from TMEM: nothing lives across the barrier) --

@@ -74,7 +74,7 @@ __global__ void stream_prep_kernel(const float* __restrict__ E, int K, int D, in
     ee[k] = a;
     float t0 = -1.0e30f, t1 = 0.0f, t2 = 0.0f;  // padded / overflowed codes never survive the filter
     if (a < CUDART_INF_F) {
-        const float h = -0.5f * a;
+        const float h = (-0.5f * kTruncC) * a;  // centred truncation error (ctvq_common.cuh)
         t0 = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
         const float r1 = h - t0;
         t1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(128 * T + 96, 1) vq_fwd_tc_stream_kernel(const
                 return ZREG ? zr[ZREG ? j : 0] : *reinterpret_cast<const float*>(zrow + j * 128 + zsw[j & 3]);
             };
             // rigorous bound on |tf32 distance - exact-chain distance|; scores are distances / -2
-            const float thr = 2.0f * (2.0f * 2.05e-3f * sqrt_approx_s(zz) * 1.0001f * emax + kWinAbs * (zz + emax * emax));
+            const float thr = 2.0f * (2.0f * kTf32Eps * sqrt_approx_s(zz) * 1.0001f * emax + kWinAbs * (zz + emax * emax));
             // Running state.  Exact distances are only needed to COMPARE candidates, and an L2 round trip per unit would stall
             // the few warps an SM has, so survivors are QUEUED (three register slots: code + an upper bound of its
             // approximate score = the running maximum when it was queued, hence non-decreasing along the queue).  A later

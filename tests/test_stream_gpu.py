@@ -165,3 +165,39 @@ def test_single_codebook_backward_at_scale(env, cfg):
     gz, ge = CO.backward(z_cpu, inds_cpu, book, 0.25, g_out, 0.7)
     assert rel_err(z.grad.cpu(), gz) < TOL
     assert rel_err(m.embedding.weight.grad.cpu(), ge.reshape(K, D)) < TOL
+
+
+def test_tf32_operands_are_truncated(env):
+    """The candidate window of every tf32 kernel is CENTRED on the mean truncation loss (ctvq_common.cuh, kTruncC /
+    kTf32Eps): that is only rigorous if tcgen05.mma kind::tf32 truncates its fp32 operands (toward zero) to 10 explicit
+    mantissa bits.  Pin it through the raw-TMEM dump of the generic kernel: a part that rounded to nearest instead would
+    return 1 + 2^-10 for the operands below and this test -- not a rare index mismatch -- would say so."""
+    import ctypes
+    pkg, _lib, O, CO = env
+    dev = torch.device("cuda:0")
+    B, D, H, W, K = 2, 32, 8, 8, 64
+    m = pkg.VectorQuantizerMS(K, D).to(dev)
+    E = torch.zeros(K, D, device=dev)
+    E[:, 0] = 1.0
+    E[1, 0] = 1.0 + 2.0 ** -11 + 2.0 ** -20          # B operand just above the rounding midpoint
+    m.embedding.weight.data = E
+    z = torch.zeros(B, D, H, W, device=dev)
+    vals = [1.0 + 2.0 ** -11 + 2.0 ** -20, 1.0 + 2.0 ** -10 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, -(1.0 + 2.0 ** -11 + 2.0 ** -20),
+            1.0 + 2.0 ** -10 - 2.0 ** -23]
+    for i, v in enumerate(vals):
+        z[0, 0, 0, i] = v
+    z[0, 0, 1, 0] = 1.0
+    dump = torch.full((128, K), float("nan"), device=dev)
+    L = _lib.lib()
+    L.ctvq_debug_set_tc_dump(ctypes.c_void_p(dump.data_ptr()))
+    try:
+        _lib.set_path(_lib.PATH_TC)
+        m(z, inds=True)
+        torch.cuda.synchronize()
+    finally:
+        L.ctvq_debug_set_tc_dump(None)
+    assert not torch.isnan(dump[: len(vals), 0]).any(), "the generic tcgen05 kernel did not run (dump untouched)"
+    for i, v in enumerate(vals):
+        trunc = float(torch.tensor(v).view(torch.int32).bitwise_and(~0x1FFF).view(torch.float32))
+        assert float(dump[i, 0]) == trunc, f"A operand {v!r}: tensor core used {float(dump[i, 0])!r}, truncation gives {trunc!r}"
+    assert float(dump[8, 1]) == 1.0, f"B operand 1 + 2^-11 + 2^-20 was not truncated to 1.0: {float(dump[8, 1])!r}"
