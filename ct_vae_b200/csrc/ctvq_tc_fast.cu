@@ -228,17 +228,30 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_fast_kernel(const
     } else {
         // =============================== epilogue warps: units (tile, codebook), rows of lane quarter ==================
         const int nunits = niter * C;
-        for (int u = wg; u < nunits; u += NWG) {
-            const int it = u / C, c = u - it * C;
-            // lane-dependent part of the swizzled z address, indexed by (channel & 3) relative to this codebook's first channel
-            uint32_t zsw[4];
+        // one warpgroup per codebook (NWG == C): the codebook of a warpgroup never changes, so everything that depends on it
+        // only is computed once (the compiler cannot see that u % C is loop-invariant)
+        constexpr bool kFixedC = (NWG == C);
+        int c = kFixedC ? wg : 0;
+        // lane-dependent part of the swizzled z address, indexed by (channel & 3) relative to this codebook's first channel
+        uint32_t zsw[4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ (x + c * CS)) & 3) << 5) + ((lane & 7) << 2);
-            const float* ee = ee_s + c * NK;
-            const uint8_t* ecb = e_s + (size_t)c * kEcb;
-            const float emax = emax_s[c];
+        for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ (x + c * CS)) & 3) << 5) + ((lane & 7) << 2);
+        const float* ee = ee_s + c * NK;
+        const uint8_t* ecb = e_s + (size_t)c * kEcb;
+        float emax = emax_s[c];
+        const bool one_seg = (p.n_seg == 1);
+        for (int u = wg; u < nunits; u += NWG) {
+            const int it = kFixedC ? (u - wg) / NWG : u / C;
+            if (!kFixedC) {
+                c = u - it * C;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) zsw[x] = ((((lane >> 3) ^ (x + c * CS)) & 3) << 5) + ((lane & 7) << 2);
+                ee = ee_s + c * NK;
+                ecb = e_s + (size_t)c * kEcb;
+                emax = emax_s[c];
+            }
             const int tile = blockIdx.x + it * gridDim.x;
-            const int seg = tile / p.tiles_per_seg;
+            const int seg = one_seg ? 0 : tile / p.tiles_per_seg;  // (a runtime division per tile otherwise)
             const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
             const long long n = row0 + quarter * 32 + lane;
             const bool valid = n < p.N;  // warp-uniform (N is a multiple of 32)
