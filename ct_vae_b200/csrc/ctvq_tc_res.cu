@@ -64,7 +64,13 @@ __device__ __forceinline__ float sqrt_approx_r(float x) {
     return r;
 }
 
-constexpr int kL2Ahead = 2;  // tiles requested into L2 ahead of their shared-memory load
+// Tiles requested into L2 ahead of their shared-memory load.  0 = the L2 request of a tile goes out right before the TMA
+// lane starts waiting for the tile's ring slot, i.e. the lead is exactly the time the slot is still busy.  Re-measured after
+// the window was centred (less epilogue time per tile): 2 tiles ahead -- the round-2 setting -- had become a liability at
+// config 3 (K=64, d=128: 0.256 ms back to back / 0.209 ms behind a backward, against 0.199 ms in every context with 0;
+// 3 and 4 tiles ahead: 0.27-0.29 ms): lines requested too early are evicted by the kernel's own 0.5 GB write stream
+// before the load arrives, and then cross HBM twice.  No request at all is 3 % slower than 0 at H*W = 256.
+constexpr int kL2Ahead = 0;
 constexpr int kCap = 128;  // pairs per (tile parity, lane quarter) list: one per thread of the four slice warps
 
 // (distance, code) as ONE 64-bit key whose unsigned order is torch.argmin's: NaN first, then ascending distance

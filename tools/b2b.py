@@ -11,7 +11,8 @@ dev = torch.device("cuda:0")
 what = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 N, D, K, C, HW, kind = {"cfg3": (1 << 20, 128, 64, 1, 64, "trained"), "cfg2": (1 << 20, 128, 64, 4, 64, "trained"),
-                        "cfg1": (1 << 20, 64, 512, 1, 256, "init")}[what]
+                        "cfg1": (1 << 20, 64, 512, 1, 256, "init"), "k16384d256": (1 << 16, 256, 16384, 1, 256, "trained"),
+                        "k1024d64": (1 << 20, 64, 1024, 1, 256, "trained"), "k16384d32": (1 << 20, 32, 16384, 1, 256, "trained")}[what]
 B = N // HW
 side = int(HW ** 0.5)
 torch.manual_seed(0)

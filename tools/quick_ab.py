@@ -24,6 +24,10 @@ PTS = {
     "k4096d128": (1 << 18, 128, 4096, 1, 256, "trained"),
     "k16384d32": (1 << 20, 32, 16384, 1, 256, "trained"),
     "k16384d256": (1 << 16, 256, 16384, 1, 256, "trained"),
+    "k1024d256": (1 << 18, 256, 1024, 1, 256, "trained"),
+    "k4096d256": (1 << 17, 256, 4096, 1, 256, "trained"),
+    "k1024d128": (1 << 19, 128, 1024, 1, 256, "trained"),
+    "k16384d128": (1 << 17, 128, 16384, 1, 256, "trained"),
 }
 dev = torch.device("cuda:0")
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
