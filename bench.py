@@ -746,7 +746,7 @@ def main():
     ]
     # DRAM traffic per launch: NOT measured by this run (it needs ncu); the figures come from the committed
     # `ncu --set full` capture of this very workload and are quoted only for the profiled batch size
-    ncu_traffic = {16384: (146948864 + 511877376, 717344000 + 497388032)}.get(B)
+    ncu_traffic = {16384: (146883584 + 512446464, 717344000 + 498355968)}.get(B)
     for i, k in enumerate(kernels):
         k["frac"] = k["gbs"] / hbm_peak
         k["traffic"] = ncu_traffic[i] if ncu_traffic else None
