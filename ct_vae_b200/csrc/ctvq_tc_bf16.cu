@@ -219,13 +219,16 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) vq_fwd_tc_bf16_kernel(const
         // =============================== epilogue warps: units (tile, codebook), rows of lane quarter ==================
         const int nunits = niter * C;
         const int rblk = (quarter & 1) * 32 + lane;  // row inside its 64-row block
+        constexpr bool kFixedC = (NWG == C);  // one warpgroup per codebook: c is loop-invariant (ctvq_tc_fast.cu)
+        const bool one_seg = (p.n_seg == 1);
         for (int u = wg; u < nunits; u += NWG) {
-            const int it = u / C, c = u - it * C;
+            const int it = kFixedC ? (u - wg) / NWG : u / C;
+            const int c = kFixedC ? wg : u - it * C;
             const float* ee = ee_s + c * NK;
             const uint8_t* ecb = e_s + (size_t)c * kEcb;
             const float emax = emax_s[c];
             const int tile = blockIdx.x + it * gridDim.x;
-            const int seg = tile / p.tiles_per_seg;
+            const int seg = one_seg ? 0 : tile / p.tiles_per_seg;  // (a runtime division per tile otherwise)
             const long long row0 = (long long)(tile - seg * p.tiles_per_seg) * kTM;
             const long long n = row0 + quarter * 32 + lane;
             const bool valid = n < p.N;  // warp-uniform (N is a multiple of 32)
