@@ -480,7 +480,7 @@ int launch_forward_tc_fast(const QuantParams& p, cudaStream_t s) {
     if (!encode_fn()) return CTVQ_E_UNSUPPORTED;
     // configs/mcq_vae.yaml: C=4 codebooks x d=32 on overlapping slices of [B,128,8,8]
     if (p.d == 32 && p.HW == 64 && p.C == 4 && p.cs == 1) {
-        // 4 epilogue warpgroups: measured 0.160 ms at 1 M rows; 5 / 6 warpgroups (80 / 72 registers) measured 0.176 / 0.180 ms
+        // 4 epilogue warpgroups: 0.160 ms at 1 M rows when measured (0.152 ms today); 5 / 6 warpgroups (80 / 72 registers) measured 0.176 / 0.180 ms
         // -- the L1/shared data pipe, not latency, is the limiter, so more warps only add contention
         return launch_fast<32, 64, 64, 4, 1, 5, 4>(p, s);
     }

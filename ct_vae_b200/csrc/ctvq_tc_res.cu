@@ -211,11 +211,12 @@ __global__ void __launch_bounds__(kRT, 1) vq_fwd_tc_res_kernel(const ResParams P
     float lsum = 0.0f;
     unsigned nnear = 0u;  // near-tie rows seen by this thread (include/ctvq.h)
     if (warp == kEW + 1) {
-        // =============================== TMA lane: slab ring, kept kL2Ahead tiles ahead in L2 ========================
+        // =============================== TMA lane: slab ring + L2 requests (kL2Ahead, see its comment) ===============
         // A slab can only be re-filled once every epilogue warp has scored its last candidate from it, which leaves less
         // than a tile time of lookahead with the 2 stages that fit beside a 128 KB codebook -- not enough to cover HBM
-        // latency.  So every tile is ALSO requested into L2 kL2Ahead tiles early (cp.async.bulk.prefetch.tensor): the
-        // late shared-memory load then completes at L2 latency.  HBM traffic is unchanged (one read per slab).
+        // latency.  So every tile is ALSO requested into L2 (cp.async.bulk.prefetch.tensor) BEFORE the lane starts waiting
+        // for its ring slot: the shared-memory load that follows the wait then completes at L2 latency.  HBM traffic stays
+        // one read per slab as long as the request is not issued too early (kL2Ahead above).
         if (lane == 0) {
             for (int nx = NSTAGE; nx < niter; ++nx) {
                 const int prev = nx - NSTAGE;
