@@ -293,10 +293,39 @@ __global__ void __launch_bounds__(kBT4, 1) vq_bwd_tma_kernel(const BwdParams p, 
         for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, NGZ); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 2 * CKD; i += kBT4) acc[i] = 0.0f;
-    for (int i = tid; i < CKD; i += kBT4) {
-        const int j = i % D, ck = i / D;
-        es[ck * ESD + j] = IO<T>::cb(__ldg(p.E[ck / K] + (size_t)(ck % K) * D + j));
+    // codebook staging: every thread's 128-bit loads are issued BEFORE its first store (one L2 / HBM round trip for the whole
+    // [C,K,D] block instead of one per unrolled group of scalar loads: the codebooks were evicted by the forward's 0.5 GB
+    // write stream, so each dependent round trip costs ~0.6 us of every launch)
+    bool e16 = (D % 4 == 0);
+#pragma unroll
+    for (int c = 0; c < C; ++c) e16 = e16 && ((reinterpret_cast<uintptr_t>(p.E[c]) & 15) == 0);
+    if (e16) {
+        constexpr int D4 = D / 4, NV = (CKD / 4 + kBT4 - 1) / kBT4;
+        float4 v[NV];
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int i = tid + u * kBT4;
+            if (i < CKD / 4) {
+                const int ck = i / D4;
+                v[u] = __ldg(reinterpret_cast<const float4*>(p.E[ck / K] + (size_t)(ck % K) * D) + (i - ck * D4));
+            }
+        }
+        for (int i = tid; i < 2 * CKD; i += kBT4) acc[i] = 0.0f;  // (scalar: the accumulators are only 8-byte aligned behind zs)
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int i = tid + u * kBT4;
+            if (i < CKD / 4) {
+                const int ck = i / D4;
+                float* dst = es + ck * ESD + 4 * (i - ck * D4);
+                dst[0] = IO<T>::cb(v[u].x); dst[1] = IO<T>::cb(v[u].y); dst[2] = IO<T>::cb(v[u].z); dst[3] = IO<T>::cb(v[u].w);
+            }
+        }
+    } else {
+        for (int i = tid; i < 2 * CKD; i += kBT4) acc[i] = 0.0f;
+        for (int i = tid; i < CKD; i += kBT4) {
+            const int j = i % D, ck = i / D;
+            es[ck * ESD + j] = IO<T>::cb(__ldg(p.E[ck / K] + (size_t)(ck % K) * D + j));
+        }
     }
     const float gl = __ldg(p.g_loss);
     const double nd = (double)p.N * (double)D;
